@@ -1,0 +1,416 @@
+// bicgstab.cu -- device-resident BiCGStab: BiCGStab::solve (src/bicg_stab.rs:35-200) and
+// BiCGStab::precond_solve (src/bicg_stab.rs:204-366).
+//
+// Same recurrence, same sign convention (r = A x - b, x -= ...), same unrolled first iteration,
+// rho restart, breakdown test and convergence test at the top of the next iteration.  The
+// reference's 11 separate vecalg passes per iteration are fused into three kernels and two SpMV
+// epilogues; every element is still computed with the reference's operations in the reference's
+// order (no FMA), only the long sums are re-ordered:
+//   S1 : ||r||, rho = <r0,r>  -> convergence / restart test, beta                (:296-319)
+//   K1 : p = (-beta w) v + beta p ; p += r ; y = M p        [Jacobi fused]        (:324-328)
+//   SpMV1: v = A y, epilogue <r0,v>                                               (:329-332)
+//   S2 : breakdown test, alpha = rho / <r0,v>                                     (:333-338)
+//   K2 : r -= alpha v ; z = M r                             [Jacobi fused]        (:341-343)
+//   SpMV2: t = A z, epilogue <t,t>, <t,r>                                         (:344-349)
+//   S3 : w = <t,r>/<t,t> (0 if <t,t>.re <= 0)                                     (:347-352)
+//   K3 : x -= alpha y ; x -= w z ; r -= w t ; partials of ||r||^2 and <r0,r>      (:355-362,296,301)
+// n-vector streams per iteration: K1 4R+2W, SpMV1 epilogue 1R, K2 3R+2W, SpMV2 epilogue 1R,
+// K3 6R+2W = 21 (Jacobi); 16 without preconditioner.
+#include "solver.cuh"
+
+namespace spb {
+
+template <typename T>
+struct BicgState {
+  StateHead h;
+  T rho, rho_old, alpha, w, beta, c_pv, nalpha, nw;
+  double rhs_norm, tol2, r0_norm_tol, r_norm, tol;
+};
+
+__device__ __forceinline__ void hist_put(StateHead& h, double* hist, long long cap, long long k, double v) {
+  if (hist && k < cap) hist[k] = v;
+  if (k + 1 > h.hist_len) h.hist_len = k + 1;
+}
+
+// ---------------------------------------------------------------- scalar kernels (1 thread)
+template <typename T>
+__global__ void bicg_s_rhs(BicgState<T>* st, const scal2* red) {
+  const double rhs_norm = sqrt(red[0].re);  // norm2(rhs), :225
+  st->rhs_norm = rhs_norm;
+  st->tol2 = st->tol * rhs_norm;            // :231
+  if (rhs_norm <= SPB_EPS) {                // :226-230
+    st->h.status = DS_ZERO_RHS;
+    st->h.res_iters = 0;
+    st->h.res_resid = rhs_norm;
+  }
+}
+
+// after r = A x - rhs, r0 = r: used for the start (:251-259) and for the restart (:315-317)
+template <typename T>
+__global__ void bicg_s_init(BicgState<T>* st, const scal2* red, double* hist, long long cap, int restart) {
+  if (restart ? st->h.status != DS_NEED_RESTART : st->h.status != DS_RUNNING) return;
+  const double rn = sqrt(red[0].re);
+  if (!restart) {
+    hist_put(st->h, hist, cap, 0, rn / st->rhs_norm);
+    if (rn <= st->tol2) {  // :252-254
+      st->h.status = DS_OK;
+      st->h.res_iters = 0;
+      st->h.res_resid = rn / st->rhs_norm;
+      return;
+    }
+    double t = rn * SPB_EPS;  // :255-256
+    st->r0_norm_tol = t * t;
+    st->rho = from_real<T>(rn * rn);  // :259
+  } else {
+    st->rho = from_real<T>(rn * rn);                              // :316
+    st->r0_norm_tol = re_of(st->rho) * SPB_EPS * SPB_EPS;         // :317
+    const T beta = mul(divi(st->rho, st->rho_old), divi(st->alpha, st->w));  // :319
+    st->beta = beta;
+    st->c_pv = mul(neg(beta), st->w);
+    st->h.status = DS_RUNNING;
+  }
+}
+
+template <typename T>
+__global__ void bicg_s1(BicgState<T>* st, const scal2* red, double* hist, long long cap) {
+  if (st->h.status != DS_RUNNING) return;
+  const long long its = ++st->h.its;
+  const double r_norm = sqrt(red[0].re);  // :296
+  st->r_norm = r_norm;
+  hist_put(st->h, hist, cap, its, r_norm / st->rhs_norm);
+  if (r_norm <= st->tol2) {  // :297-299
+    st->h.status = DS_OK;
+    st->h.res_iters = its;
+    st->h.res_resid = r_norm / st->rhs_norm;
+    return;
+  }
+  st->rho_old = st->rho;             // :300
+  st->rho = from_scal2<T>(red[1]);   // :301
+  if (abs_of(st->rho) < st->r0_norm_tol) {  // :304
+    st->h.status = DS_NEED_RESTART;
+    return;
+  }
+  const T beta = mul(divi(st->rho, st->rho_old), divi(st->alpha, st->w));  // :319
+  st->beta = beta;
+  st->c_pv = mul(neg(beta), st->w);  // -beta * w, :324
+}
+
+template <typename T>
+__global__ void bicg_s2(BicgState<T>* st, const scal2* red, int first) {
+  if (st->h.status != DS_RUNNING) return;
+  const T tmp = from_scal2<T>(red[0]);  // conj_dot(r0, v), :332
+  if (!first && abs_of(tmp) <= 0.0) {   // :333-336 (the unrolled first iteration has no test, :266)
+    st->h.status = DS_BREAKDOWN;
+    st->h.res_iters = st->h.its;
+    return;
+  }
+  st->alpha = divi(st->rho, tmp);  // :338
+  st->nalpha = neg(st->alpha);
+}
+
+template <typename T>
+__global__ void bicg_s3(BicgState<T>* st, const scal2* red) {
+  if (st->h.status != DS_RUNNING) return;
+  const T tt = from_scal2<T>(red[0]);  // conj_dot(t, t), :347
+  st->w = re_of(tt) > 0.0 ? divi(from_scal2<T>(red[1]), tt) : zero_of<T>();  // :348-352
+  st->nw = neg(st->w);
+}
+
+// ---------------------------------------------------------------- vector kernels
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads)
+bicg_k_init(const BicgState<T>* st, int restart, int64_t n, const T* rhs, T* r, T* r0, T* partials) {
+  T e0 = zero_of<T>();
+  if (restart ? st->h.status == DS_NEED_RESTART : st->h.status == DS_RUNNING) {
+    const T m1 = neg(one_of<T>());
+    SPB_GRID_STRIDE(i, n) {
+      const T ri = add(r[i], mul(rhs[i], m1));  // axpy(-1, rhs, r), :246
+      r[i] = ri;
+      r0[i] = ri;                               // :249
+      e0 = add(e0, from_real<T>(square(ri)));   // norm2, :251
+    }
+  }
+  write_partials(e0, zero_of<T>(), partials);
+}
+
+template <typename T, typename V, bool FIRST, bool WRITE_Y>
+__global__ void __launch_bounds__(kVecThreads)
+bicg_k1(const BicgState<T>* st, int64_t n, const T* v, T* p, const T* r, T* y, const V* dinv) {
+  if (st->h.status != DS_RUNNING) return;
+  const T c_pv = st->c_pv, beta = st->beta, one = one_of<T>();
+  SPB_GRID_STRIDE(i, n) {
+    T pi;
+    if (FIRST) {
+      pi = r[i];  // p = r, :261
+    } else {
+      pi = add(mul(v[i], c_pv), mul(p[i], beta));  // axpby(-beta w, v, beta, p), :324
+      pi = add(pi, mul(r[i], one));                // axpy(1, r, p), :325
+    }
+    p[i] = pi;
+    if (WRITE_Y) y[i] = mul_diag(pi, dinv[i]);     // y = M p, :328 (src/precond.rs:50)
+  }
+}
+
+template <typename T, typename V, bool WRITE_Z>
+__global__ void __launch_bounds__(kVecThreads)
+bicg_k2(const BicgState<T>* st, int64_t n, T* r, const T* v, T* z, const V* dinv) {
+  if (st->h.status != DS_RUNNING) return;
+  const T nalpha = st->nalpha;
+  SPB_GRID_STRIDE(i, n) {
+    const T ri = add(r[i], mul(v[i], nalpha));  // axpy(-alpha, v, r), :341
+    r[i] = ri;
+    if (WRITE_Z) z[i] = mul_diag(ri, dinv[i]);  // z = M r, :343
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kVecThreads)
+bicg_k3(const BicgState<T>* st, int64_t n, T* x, const T* y, const T* z, T* r, const T* t, const T* r0,
+        T* partials) {
+  T e0 = zero_of<T>(), e1 = zero_of<T>();
+  if (st->h.status == DS_RUNNING) {
+    const T nalpha = st->nalpha, nw = st->nw;
+    SPB_GRID_STRIDE(i, n) {
+      const T zi = z[i];  // may alias r (no preconditioner): read before r is updated
+      T xi = add(x[i], mul(y[i], nalpha));  // axpy(-alpha, y, x), :355
+      xi = add(xi, mul(zi, nw));            // axpy(-w, z, x), :357
+      x[i] = xi;
+      const T ri = add(r[i], mul(t[i], nw));  // axpy(-w, t, r), :362
+      r[i] = ri;
+      e0 = add(e0, from_real<T>(square(ri)));      // next norm2(r), :296
+      e1 = add(e1, mul(conj_of(r0[i]), ri));       // next conj_dot(r0, r), :301
+    }
+  }
+  write_partials(e0, e1, partials);
+}
+
+// ---------------------------------------------------------------- host driver
+template <typename T>
+struct BicgStab : spb_solver {
+  DevBuf ws;        // 7 n T  (src/bicg_stab.rs:28)
+  DevBuf partials;  // T [2 * max grid]
+  DevBuf red;       // scal2 [2]
+  DevBuf state;     // BicgState<T>
+  DevBuf hist_d;
+
+  BicgStab(spb_op* A_, int64_t size_) {
+    A = A_;
+    ctx = A_->ctx;
+    kind = 0;
+    dtype = ScalarTraits<T>::dtype;
+    size = size_;
+    ws.alloc(sizeof(T) * 7 * (size_t)std::max<int64_t>(size, 1));
+    SPB_CUDA(cudaMemsetAsync(ws.p, 0, ws.bytes, ctx->stream));
+    partials.alloc(sizeof(T) * 2 * (size_t)(vec_max_grid(ctx) + 1));
+    red.alloc(sizeof(scal2) * 2);
+    state.alloc(sizeof(BicgState<T>));
+  }
+
+  int solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_iter, double tol, int64_t* iters,
+                double* resid, double* hist, int64_t hist_cap, int64_t* hist_len) override;
+};
+
+template <typename T>
+int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_iter, double tol,
+                           int64_t* iters, double* resid, double* hist, int64_t hist_cap,
+                           int64_t* hist_len) {
+  Ctx* c = ctx;
+  const int64_t n = size;
+  const T* rhs = (const T*)d_rhs;
+  T* x = (T*)d_x;
+  if (A->kind != OP_CSR) SPB_FAIL(SPB_INVALID_ARG, "BiCGStab operator must be a CSR matrix");
+  auto* Am = static_cast<CsrMat<T>*>(A);
+  if (Am->n_local != n) {
+    set_last_error("Input vec dimension doesn't match the matrix size");
+    return SPB_INCOMPATIBLE_FORMAT;
+  }
+  if (M && M->n_local != n) SPB_FAIL(SPB_DIM_MISMATCH, "preconditioner dimension mismatch");
+  const PcMode pcm = pc_mode_of<T>(M);
+  T* w0 = bufptr<T>(ws);
+  T *r = w0, *r0 = w0 + n, *p = w0 + 2 * n, *y = w0 + 3 * n, *v = w0 + 4 * n, *t = w0 + 5 * n, *z = w0 + 6 * n;
+  if (pcm == PCM_NONE) {  // solve(): y is p, z is r (src/bicg_stab.rs:65-71, 116)
+    y = p;
+    z = r;
+  }
+  const void* dinv = (pcm == PCM_JACOBI || pcm == PCM_JACOBI_REAL) ? static_cast<DiagOp<T>*>(M)->dinv.p : nullptr;
+  auto* st = bufptr<BicgState<T>>(state);
+  scal2* redp = bufptr<scal2>(red);
+  T* parts = bufptr<T>(partials);
+  const int grid = vec_grid(c, n);
+  const long long cap = hist ? std::min<int64_t>(hist_cap, max_iter + 1) : 0;
+  double* hd = nullptr;
+  if (cap > 0) {
+    hist_d.ensure(sizeof(double) * cap);
+    hd = bufptr<double>(hist_d);
+  }
+
+  BicgState<T> init;
+  memset(&init, 0, sizeof(init));
+  init.h.status = DS_RUNNING;
+  init.tol = tol;
+  SPB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+
+  auto scalar = [&](auto kernel, auto... args) {
+    LaunchScope ls(c, FAM_SCALAR);
+    kernel<<<1, 1, 0, c->stream>>>(args...);
+    check_launch("bicg scalar kernel");
+  };
+  auto reduce_vec = [&]() {  // per-block partials of a vector kernel -> red (all ranks)
+    finalize_partials<T>(c, parts, grid, redp);
+    allreduce_sum(c, (double*)redp, 4);
+  };
+  auto reduce_spmv = [&]() {
+    Am->finalize_epilogue();
+    allreduce_sum(c, (double*)bufptr<scal2>(Am->red), 4);
+  };
+  auto k_init = [&](int restart) {
+    LaunchScope ls(c, FAM_VEC);
+    bicg_k_init<T><<<grid, kVecThreads, 0, c->stream>>>(st, restart, n, rhs, r, r0, parts);
+    check_launch("bicg_k_init");
+  };
+  auto k1 = [&](bool first) {
+    {
+      LaunchScope ls(c, FAM_VEC);
+      if (pcm == PCM_JACOBI) {
+        if (first) bicg_k1<T, T, true, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)dinv);
+        else bicg_k1<T, T, false, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)dinv);
+      } else if (pcm == PCM_JACOBI_REAL) {
+        if (first) bicg_k1<T, double, true, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const double*)dinv);
+        else bicg_k1<T, double, false, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const double*)dinv);
+      } else {
+        if (first) bicg_k1<T, T, true, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)nullptr);
+        else bicg_k1<T, T, false, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)nullptr);
+      }
+      check_launch("bicg_k1");
+    }
+    if (pcm == PCM_GENERIC) op_apply<T>(M, p, y);
+  };
+  auto k2 = [&]() {
+    {
+      LaunchScope ls(c, FAM_VEC);
+      if (pcm == PCM_JACOBI) bicg_k2<T, T, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const T*)dinv);
+      else if (pcm == PCM_JACOBI_REAL) bicg_k2<T, double, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const double*)dinv);
+      else bicg_k2<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const T*)nullptr);
+      check_launch("bicg_k2");
+    }
+    if (pcm == PCM_GENERIC) op_apply<T>(M, r, z);
+  };
+  auto tail = [&](bool first) {  // everything of an iteration after the S1 test
+    k1(first);
+    Am->mul(y, v, EPI_DOT_WY, r0, false);
+    reduce_spmv();
+    scalar(bicg_s2<T>, st, bufptr<scal2>(Am->red), first ? 1 : 0);
+    k2();
+    Am->mul(z, t, EPI_TT_TR, r, false);
+    reduce_spmv();
+    scalar(bicg_s3<T>, st, bufptr<scal2>(Am->red));
+    {
+      LaunchScope ls(c, FAM_VEC);
+      bicg_k3<T><<<grid, kVecThreads, 0, c->stream>>>(st, n, x, y, z, r, t, r0, parts);
+      check_launch("bicg_k3");
+    }
+    reduce_vec();
+  };
+
+  int rc = SPB_OK;
+  Poller poller(c);
+  StateHead hd_host;
+  c->gate = nullptr;
+  try {
+    // ||b||                                                           (:225-231)
+    vec_reduce<T>(c, 2, n, rhs, rhs, parts, redp);
+    allreduce_sum(c, (double*)redp, 4);
+    scalar(bicg_s_rhs<T>, st, redp);
+    poller.post(st);
+    poller.drain(&hd_host);
+    if (hd_host.status == DS_ZERO_RHS) {
+      SPB_CUDA(cudaMemsetAsync(x, 0, sizeof(T) * n, c->stream));  // x := 0
+      SPB_CUDA(cudaStreamSynchronize(c->stream));
+      *iters = 0;
+      *resid = hd_host.res_resid;
+      if (hist_len) *hist_len = 0;
+      return SPB_OK;
+    }
+    c->gate = &st->h.status;
+    Am->mul(x, r, EPI_NONE, nullptr, false);  // r = A x            (:244)
+    k_init(0);                                // r -= rhs, r0 = r   (:246-251)
+    reduce_vec();
+    scalar(bicg_s_init<T>, st, redp, hd, cap, 0);
+    tail(true);  // unrolled first iteration                         (:260-293)
+
+    const int64_t target = max_iter - 1;  // loop iterations 1 .. max_iter-1  (:295)
+    int64_t launched = 0;                 // S1 launches that took effect
+    bool done = false;
+    auto launch_iter = [&]() {
+      scalar(bicg_s1<T>, st, redp, hd, cap);
+      tail(false);
+      ++launched;
+    };
+    auto handle = [&](const StateHead& h) {
+      if (h.status == DS_RUNNING) return;
+      if (h.status == DS_NEED_RESTART) {
+        // rho restart (:304-318).  Everything queued after the pausing S1 was a no-op; drain
+        // it, redo r = A x - rhs, r0 = r, rho, beta on the device and resume iteration h.its.
+        StateHead last;
+        poller.drain(&last);
+        c->gate_value = DS_NEED_RESTART;
+        Am->mul(x, r, EPI_NONE, nullptr, false);
+        k_init(1);
+        reduce_vec();
+        scalar(bicg_s_init<T>, st, redp, hd, cap, 1);
+        c->gate_value = DS_RUNNING;
+        launched = h.its;
+        tail(false);
+        return;
+      }
+      done = true;
+    };
+    while (!done) {
+      StateHead h;
+      if (launched < target) {
+        const int64_t chunk = std::min<int64_t>(poll, target - launched);
+        for (int64_t i = 0; i < chunk; ++i) launch_iter();
+        poller.post(st);
+        if (poller.wait_oldest(&h)) handle(h);  // lags one chunk behind: the queue never drains
+      } else {
+        if (!poller.drain(&h)) {
+          poller.post(st);
+          poller.drain(&h);
+        }
+        handle(h);
+        if (!done && h.status == DS_RUNNING && launched >= target) break;  // exhausted (:365)
+      }
+    }
+    c->gate = nullptr;
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    // final, authoritative read of the state
+    poller.post(st);
+    poller.drain(&hd_host);
+    if (hd_host.status == DS_OK) {
+      *iters = hd_host.res_iters;
+      *resid = hd_host.res_resid;
+      rc = SPB_OK;
+    } else if (hd_host.status == DS_BREAKDOWN) {
+      *iters = hd_host.res_iters;
+      rc = SPB_BREAKDOWN;
+    } else {
+      *iters = max_iter;
+      rc = SPB_INSUFFICIENT_ITER;
+    }
+    const int64_t hl = hd_host.hist_len;
+    if (hist_len) *hist_len = hl;
+    if (hd && hl > 0)
+      SPB_CUDA(cudaMemcpy(hist, hd, sizeof(double) * std::min<int64_t>(hl, cap), cudaMemcpyDeviceToHost));
+  } catch (...) {
+    c->gate = nullptr;
+    throw;
+  }
+  return rc;
+}
+
+spb_solver* make_bicgstab(spb_op* A, int64_t size) {
+  if (A->dtype == SPB_F64) return new BicgStab<double>(A, size);
+  return new BicgStab<cplx>(A, size);
+}
+
+}  // namespace spb

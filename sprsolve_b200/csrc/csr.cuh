@@ -1,0 +1,81 @@
+// csr.cuh -- device-resident CSR operator: the drop-in for MklMat<T> / CsMatI<T,i32>
+// (src/mkl_mat.rs:15-22, src/mat.rs:47-183).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace spb {
+
+// What a SpMV launch folds into its epilogue (each replaces a separate vecalg::conj_dot pass).
+enum SpmvEpiMode {
+  EPI_NONE = 0,
+  EPI_DOT_WY = 1,  // slot0 = sum conj(w_i) * y_i            (mul_vec_dot: w = v_in; <r0,v>: w = r0)
+  EPI_TT_TR = 2    // slot0 = sum conj(y_i) * y_i, slot1 = sum conj(y_i) * w_i   (<t,t>, <t,r>)
+};
+
+struct HaloPeer {
+  int rank;
+  int64_t send_off, send_cnt;  // into sendbuf / send_idx
+  int64_t recv_off, recv_cnt;  // into halo
+};
+
+template <typename T>
+struct CsrMat : spb_op {
+  int64_t nnz = 0;
+  bool ip64 = false;
+  DevBuf indptr;  // int32 or int64 [n_local+1]
+  DevBuf cols;    // int32 [nnz + pad], LOCAL column ids: [0,n_local) owned, [n_local, n_local+n_halo) halo
+  DevBuf vals;    // T [nnz + pad]
+  int64_t max_row = 0;
+
+  // --- analysis (the mkl_sparse_optimize analogue): nnz-balanced row tiles -----------------
+  int cfg = 0;           // kernel configuration (threads, tile)
+  int64_t span = 0;      // tile t = rows whose first nnz lies in [t*span, (t+1)*span)
+  int64_t ntiles = 0;
+  DevBuf tile_row;       // int32 [ntiles+1]
+  DevBuf partials;       // T [2 * max grid], per-block epilogue partial sums
+  DevBuf red;            // scal2[2]: finalised epilogue sums
+
+  // --- row-block partition (multi-GPU) ------------------------------------------------------
+  int64_t n_halo = 0;
+  DevBuf halo;               // T [n_halo]: remote x entries, grouped by owner rank
+  DevBuf sendbuf;            // T [total send]
+  DevBuf send_idx;           // int32 [total send]: local indices to pack
+  std::vector<HaloPeer> peers;
+  std::vector<int32_t> halo_cols_global;  // sorted global ids of the halo slots (host copy)
+  DevBuf tiles_interior, tiles_boundary;  // int32 tile lists (boundary = touches a halo column)
+  int64_t n_tiles_interior = 0, n_tiles_boundary = 0;
+
+  // --- host-slice staging (trait methods on &[T]) --------------------------------------------
+  DevBuf stage_in, stage_out;
+
+  void analyze();
+  // y = A x (x, y device pointers to LOCAL vectors).  conj_in: multiply by conj(x) (CSMinRes,
+  // src/cs_minres.rs:99-101, without materialising tvec).  Epilogue sums land in `red` after
+  // finalize_epilogue() (local sum only; the caller all-reduces when distributed).
+  void mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in);
+  int64_t last_partial_blocks = 0;
+  // Sums the per-block partials of the last mul() into red[0], red[1] (device).  Local sums.
+  void finalize_epilogue();
+};
+
+template <typename T>
+CsrMat<T>* csr_from_host(Ctx* ctx, int64_t n_global, int64_t row_begin, int64_t row_end,
+                         const void* indptr, int indptr_bits, const int32_t* indices,
+                         const void* values);
+template <typename T>
+CsrMat<T>* csr_from_stencil(Ctx* ctx, int kind, int64_t nx, int64_t ny, int64_t nz,
+                            const double* params, int nparams);
+
+// dist.cu: turn GLOBAL column ids into local + halo ids, build the exchange plan.
+template <typename T>
+void csr_localize(CsrMat<T>* m);
+template <typename T>
+void classify_tiles(CsrMat<T>* m);  // interior / boundary tile lists (after analyze's tiling)
+template <typename T>
+void halo_exchange_begin(CsrMat<T>* m, const T* x);  // pack + send/recv on the comm stream
+template <typename T>
+void halo_exchange_wait(CsrMat<T>* m);               // compute stream waits for the halo
+
+}  // namespace spb

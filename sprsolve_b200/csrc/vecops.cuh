@@ -1,0 +1,56 @@
+// vecops.cuh -- device vector algebra: the vecalg module (src/vecalg.rs:19-144, fallbacks
+// :556-605) on device pointers, plus the pieces the fused solver kernels share.
+#pragma once
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace spb {
+
+static const int kVecThreads = 256;
+
+inline int vec_grid(const Ctx* c, int64_t n) {
+  // persistent-style grid: a multiple of the SM count, every CTA grid-strides
+  const int64_t want = ceil_div(n, kVecThreads);
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+inline int64_t vec_max_grid(const Ctx* c) { return (int64_t)c->sm_count * 8; }
+
+#define SPB_GRID_STRIDE(i, n)                                                        \
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n);          \
+       i += (int64_t)gridDim.x * blockDim.x)
+
+// Per-block partial sums of up to two quantities -> partials[2*block + slot].
+template <typename T>
+__device__ __forceinline__ void write_partials(T e0, T e1, T* partials) {
+  __shared__ T scratch[32];
+  e0 = block_sum(e0, scratch);
+  e1 = block_sum(e1, scratch);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = e0;
+    partials[2 * blockIdx.x + 1] = e1;
+  }
+}
+
+// Fixed-order sum of the block partials into red[0], red[1] (one tiny CTA).
+template <typename T>
+void finalize_partials(Ctx* c, const T* partials, int64_t nblocks, scal2* red);
+
+// vecalg on device pointers ---------------------------------------------------------------
+// kind: 0 = dot (no conjugate, vecalg.rs:557-561), 1 = conj_dot (:564-568), 2 = sum |x|^2 (:601-605)
+template <typename T>
+void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, T* partials, scal2* red);
+template <typename T>
+void vec_axpy(Ctx* c, int64_t n, T a, const T* x, T* y);
+template <typename T>
+void vec_axpby(Ctx* c, int64_t n, T a, const T* x, T b, T* y);
+template <typename T>
+void vec_scale(Ctx* c, int64_t n, T a, T* x);
+template <typename T>
+void vec_rscale(Ctx* c, int64_t n, double a, T* x);
+template <typename T>
+void vec_conj(Ctx* c, int64_t n, const T* x, T* out);
+template <typename T>
+void vec_zero(Ctx* c, int64_t n, T* x);
+
+}  // namespace spb

@@ -1,0 +1,70 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol
+include/sprsolve_b200.h declares, fails loudly without a GPU, and never touches the oracle."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "sprsolve_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(spb_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from sprsolve_b200 import _ffi, build
+
+    lib_path = build.build()
+    out = subprocess.run(["nm", "-D", "--defined-only", lib_path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (spb_[a-z0-9_]+)", out))
+    declared = _header_symbols()
+    assert declared, "no declarations parsed"
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert sorted(_ffi.SIGNATURES) == declared  # the ctypes binding covers exactly the header
+    _ffi.lib()
+
+
+def test_compiled_for_sm_100a_only():
+    from sprsolve_b200 import build
+
+    out = subprocess.run(["cuobjdump", "--list-elf", build.build()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sprsolve_b200 as sp
+
+    with pytest.raises(sp.BackendError) as e:
+        sp.Context(0)
+    assert "103" in str(e.value)  # SPB_NO_DEVICE
+
+
+def test_product_never_references_the_oracle():
+    pat = re.compile(r"oracle|liboracle|sprs_oracle", re.I)
+    bad = []
+    for base in ("sprsolve_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            if os.path.basename(dirpath) in ("build", "lib", "__pycache__"):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    for m in pat.finditer(txt):
+                        line = txt[: m.start()].count("\n") + 1
+                        ctx = txt.splitlines()[line - 1]
+                        if "oracle/sprs_oracle.h" in ctx and ctx.lstrip().startswith(("*", "//")):
+                            continue  # a doc pointer to the history definition
+                        bad.append(f"{f}:{line}: {ctx.strip()}")
+    assert not bad, bad
+    out = subprocess.run(["ldd", os.path.join(ROOT, "sprsolve_b200", "lib", "libsprsolve_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out

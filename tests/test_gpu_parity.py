@@ -1,0 +1,503 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): SpMV / Jacobi / Gauss-Seidel element-wise results are compared
+BIT-EXACTLY (the kernels keep the reference's per-row sequential accumulation and never fuse
+a*b+c); solver residual histories within 1e-10 relative over the first 50 iterations, final
+solution within the solve tolerance, iteration counts within +-2 % (only the order of the long
+dot-product sums differs).  Reference paths are relative to the reference crate root.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import fixtures as fx
+
+pytestmark = pytest.mark.gpu
+
+HIST_RTOL = 1e-10  # north_star: residual history within 1e-10 relative over the first 50 iterations
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import sprsolve_b200 as s
+
+    s.default_context()  # raises loudly without a GPU / built extension
+    return s
+
+
+def to_gpu(sp, A):
+    return sp.GpuCsrMat.new(A.indptr, A.indices, A.data, shape=(A.n, A.ncols))
+
+
+def assert_hist(h_gpu, h_orc, k=50):
+    m = min(k, len(h_orc), len(h_gpu))
+    assert m > 0
+    a, b = np.asarray(h_gpu[:m]), np.asarray(h_orc[:m])
+    assert np.all(np.abs(a - b) <= HIST_RTOL * np.abs(b)), np.max(np.abs(a - b) / np.abs(b))
+
+
+def assert_iters(it_gpu, it_orc):
+    assert abs(it_gpu - it_orc) <= max(1, int(np.ceil(0.02 * it_orc))), (it_gpu, it_orc)
+
+
+# ------------------------------------------------------------------ SpMV known answers
+def test_kat_dense_csr_mat(sp):
+    """src/mat.rs:232-255 / src/mkl_mat.rs:342-365, includes an empty row."""
+    A = to_gpu(sp, fx.kat_csr())
+    y = np.full(5, 7.0)
+    A.mul_vec(np.array(fx.KAT_X), y)
+    assert np.all(np.abs(y - np.array(fx.KAT_Y)) < 1e-8) and y[1] == 0.0
+    assert A.size() == 5
+
+
+def test_kat_i32_indptr(sp):
+    """src/mat.rs:258-280: i32 index arrays (CsMatI<f64,i32>, what MklMat::new consumes)."""
+    A = sp.GpuCsrMat.new(np.array(fx.KAT_INDPTR, np.int32), np.array(fx.KAT_INDICES, np.int32), np.array(fx.KAT_DATA))
+    y = np.zeros(5)
+    A.mul_vec(np.array(fx.KAT_X), y)
+    assert np.all(np.abs(y - np.array(fx.KAT_Y)) < 1e-8)
+
+
+def test_kat_complex(sp):
+    """src/mkl_mat.rs:368-405."""
+    A = to_gpu(sp, fx.kat_csr(np.complex128))
+    y = np.zeros(5, np.complex128)
+    A.mul_vec(np.array(fx.KAT_X, np.complex128), y)
+    assert np.all(np.abs(y.real - np.array(fx.KAT_Y)) < 1e-8) and np.all(np.abs(y.imag - np.array(fx.KAT_Y)) < 1e-8)
+
+
+def test_kat_exact_integers(sp):
+    """src/mkl_mat.rs:408-430, eps 1e-16."""
+    A = to_gpu(sp, fx.kat2_csr())
+    y = np.zeros(5)
+    A.mul_vec(np.array(fx.KAT2_X), y)
+    assert np.all(np.abs(y - np.array(fx.KAT2_Y)) < 1e-16)
+
+
+def test_kat_mul_vec_dot(sp, orc):
+    """src/mkl_mat.rs:433-463: dotmv == conj_dot(x, A x)."""
+    A = to_gpu(sp, fx.kat_csr(np.complex128))
+    x = np.array(fx.KAT_X, np.complex128) * (1 + 0.5j)
+    y = np.zeros(5, np.complex128)
+    d = A.mul_vec_dot(x, y)
+    yo, do = orc.spmv_dot(fx.kat_csr(np.complex128), x)
+    assert np.array_equal(y, yo)
+    assert abs(d - do) <= 1e-15 * abs(do)
+
+
+def test_dimension_mismatch_and_formats(sp):
+    A = to_gpu(sp, fx.kat_csr())
+    with pytest.raises(sp.DimensionMismatch):  # panic!("Dimension mismatch"), src/mat.rs:50-52
+        A.mul_vec(np.zeros(4), np.zeros(5))
+    with pytest.raises(sp.DimensionMismatch):
+        A.mul_vec(np.zeros(5), np.zeros(4))
+    with pytest.raises(sp.IncompatibleMatrixFormat):  # assert_eq!(ncol, nrow), src/mkl_mat.rs:37
+        sp.GpuCsrMat.new(np.array([0, 1, 2]), np.array([0, 1]), np.array([1.0, 2.0]), shape=(2, 3))
+    P = sp.DiagPrecond.new(np.ones(5))
+    with pytest.raises(NotImplementedError):  # unimplemented!(), src/precond.rs:55-62
+        P.mul_vec_dot(np.zeros(5), np.zeros(5))
+    with pytest.raises(sp.DimensionMismatch):  # src/precond.rs:39-41
+        P.mul_vec(np.zeros(4), np.zeros(4))
+
+
+# ------------------------------------------------------------------ SpMV vs oracle, bit exact
+def _rand_vec(n, dtype, seed=12345):
+    rng = np.random.default_rng(seed)
+    v = rng.uniform(-1, 1, n)
+    if np.dtype(dtype).kind == "c":
+        v = v + 1j * rng.uniform(-1, 1, n)
+    return v.astype(dtype)
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize(
+    "make",
+    [
+        lambda o: o.gen_lap3d7(24, 20, 17, shift=0.05),
+        lambda o: o.gen_lap3d7(15, 14, 13, shift=0.5 + 0.5j, dtype=np.complex128),
+        lambda o: o.gen_convdiff27(13, 11, 10),
+        lambda o: o.gen_dirichlet2d(40)[0],
+    ],
+    ids=["lap7_f64", "helmholtz_c128", "convdiff27", "dirichlet2d"],
+)
+def test_spmv_bit_exact(sp, orc, make, cfg):
+    os.environ["SPB_SPMV_CFG"] = str(cfg)
+    try:
+        A = make(orc)
+        G = to_gpu(sp, A)
+        x = _rand_vec(A.n, A.dtype)
+        y = np.zeros(A.n, A.dtype)
+        G.mul_vec(x, y)
+        assert np.array_equal(y, orc.spmv(A, x))
+        y2 = np.zeros(A.n, A.dtype)
+        d = G.mul_vec_dot(x, y2)
+        yo, do = orc.spmv_dot(A, x)
+        assert np.array_equal(y2, yo)
+        assert abs(d - do) <= 1e-13 * max(abs(do), 1.0)
+    finally:
+        os.environ.pop("SPB_SPMV_CFG", None)
+
+
+def test_spmv_ragged_and_long_rows(sp, orc):
+    """Ragged rows, empty rows, an all-empty matrix and rows longer than the staging tile
+    (those take the block-strided path: summation order differs, values to 1e-13)."""
+    import scipy.sparse as spa
+
+    rng = np.random.default_rng(7)
+    n = 3000
+    M = spa.random(n, n, density=0.002, random_state=3, format="lil")
+    M[5, :] = rng.uniform(-1, 1, n)        # one dense row (> 2048 nnz)
+    M[17, ::2] = 1.5                        # 1500 nnz
+    M[100:140, :] = 0                       # empty rows
+    M = M.tocsr()
+    M.sort_indices()
+    A = orc.Csr(n, M.indptr, M.indices, M.data)
+    G = to_gpu(sp, A)
+    x = _rand_vec(n, np.float64)
+    y = np.zeros(n)
+    G.mul_vec(x, y)
+    yo = orc.spmv(A, x)
+    short = np.diff(A.indptr) <= 512
+    assert np.array_equal(y[short], yo[short])
+    assert np.allclose(y, yo, rtol=1e-13, atol=1e-13)
+    E = orc.Csr(4, np.zeros(5, np.int64), np.zeros(0, np.int32), np.zeros(0))
+    GE = to_gpu(sp, E)
+    y = np.ones(4)
+    GE.mul_vec(np.ones(4), y)
+    assert np.all(y == 0.0)
+
+
+def test_generators_match_oracle(sp, orc):
+    """On-device generators == the oracle's (reference generator: src/main.rs:53-88)."""
+    cases = [
+        (sp.STENCIL_DIRICHLET2D, (33, 33, 1), (), np.float64, orc.gen_dirichlet2d(33)[0]),
+        (sp.STENCIL_LAP3D7, (9, 8, 7), (0.05,), np.float64, orc.gen_lap3d7(9, 8, 7, shift=0.05)),
+        (sp.STENCIL_LAP3D7, (6, 7, 8), (0.5, 0.5), np.complex128, orc.gen_lap3d7(6, 7, 8, shift=0.5 + 0.5j, dtype=np.complex128)),
+        (sp.STENCIL_CONVDIFF27, (9, 8, 7), (1.0, 0.5, 0.25), np.float64, orc.gen_convdiff27(9, 8, 7)),
+    ]
+    for kind, (nx, ny, nz), params, dt, A in cases:
+        G = sp.GpuCsrMat.from_stencil(kind, nx, ny, nz, params=params, dtype=dt)
+        ip, idx, dat = G.download()
+        assert np.array_equal(ip, A.indptr) and np.array_equal(idx, A.indices) and np.array_equal(dat, A.data)
+        assert np.array_equal(G.diagonal(), A.diagonal())
+
+
+# ------------------------------------------------------------------ vecalg (src/vecalg.rs tests)
+def test_vecalg_kats(sp, orc):
+    va = sp.vecalg
+    assert va.norm2(np.ones(25)) == pytest.approx(5.0, abs=1e-15)        # vecalg.rs:613-626
+    assert va.norm2(np.full(50, 1 + 1j)) == pytest.approx(10.0, abs=1e-14)
+    assert va.dot(np.ones(6), np.arange(1.0, 7.0)) == 21.0               # :629-638
+    assert va.conj_dot(np.full(100, 1.0), np.full(100, 2.0)) == 200.0    # :641-645
+    r = va.conj_dot(np.full(100, 4 + 3j), np.full(100, 2 - 3j))          # doctest :36-46
+    t = np.conj(4 + 3j) * (2 - 3j) * 100
+    assert r == pytest.approx(t, abs=1e-12)
+    r = va.dot(np.full(100, 2 + 3j), np.full(100, 2 - 3j))               # no conjugate, :712-719
+    assert r.real == pytest.approx(1300.0) and r.imag == pytest.approx(0.0)
+    a = np.ones(100)
+    va.scale(1.5, a)                                                     # :659-674
+    assert np.all(a == 1.5)
+    a = np.full(100, 2 + 3j)
+    va.scale(1.2 + 4.8j, a)
+    assert np.allclose(a, (2 + 3j) * (1.2 + 4.8j))
+    b = np.full(100, 1 + 2j)
+    va.rscale(9.0, b)                                                    # :832-841
+    assert np.all(b == 9 + 18j)
+    c = np.zeros(100, np.complex128)
+    va.conj(np.full(100, 3 + 2j), c)                                     # :803-830
+    assert np.all(c == 3 - 2j)
+    a, b = np.ones(128), np.zeros(128)
+    for _ in range(4):
+        va.axpy(2.0, a, b)                                               # :775-785 (f64 replay)
+    assert np.all(b == 8.0)
+    for _ in range(3):
+        va.axpby(2.0, a, -1.0, b)                                        # :787-801
+    assert np.all(b == -6.0)
+    a = np.full(6, 1j)
+    b = np.arange(6).astype(np.complex128)
+    va.axpy(1j, a, b)                                                    # :750-772
+    assert np.allclose(b, np.arange(6) - 1.0)
+
+
+def test_vecalg_vs_oracle(sp, orc):
+    va = sp.vecalg
+    for dt in (np.float64, np.complex128):
+        n = 100_003
+        x, y = _rand_vec(n, dt, 1), _rand_vec(n, dt, 2)
+        a, b = (0.3 - 1.1j, -0.7 + 0.2j) if np.dtype(dt).kind == "c" else (0.3, -0.7)
+        for f in ("dot", "conj_dot"):
+            g, o = getattr(va, f)(x, y), getattr(orc, f)(x, y)
+            assert abs(g - o) <= 1e-12 * n ** 0.5
+        assert va.norm2(x) == pytest.approx(orc.norm2(x), rel=1e-13)
+        yg, yo = y.copy(), y.copy()
+        va.axpy(a, x, yg), orc.axpy(a, x, yo)
+        assert np.array_equal(yg, yo)  # element-wise ops are bit exact
+        va.axpby(a, x, b, yg), orc.axpby(a, x, b, yo)
+        assert np.array_equal(yg, yo)
+        va.scale(b, yg), orc.scale(b, yo)
+        assert np.array_equal(yg, yo)
+        va.rscale(1.7, yg), orc.rscale(1.7, yo)
+        assert np.array_equal(yg, yo)
+
+
+# ------------------------------------------------------------------ preconditioner apply
+def test_jacobi_apply_bit_exact(sp, orc):
+    A = orc.gen_convdiff27(8, 7, 6)
+    v = _rand_vec(A.n, np.float64)
+    out = np.zeros(A.n)
+    sp.DiagPrecond.new(A.diagonal()).mul_vec(v, out)
+    assert np.array_equal(out, orc.diag_apply(A.diagonal(), v))
+    out2 = np.zeros(A.n)
+    sp.DiagPrecond.from_matrix(to_gpu(sp, A)).mul_vec(v, out2)
+    assert np.array_equal(out2, out)
+    Ah, _, dreal, _ = fx.hermitian_grid(8, 8)
+    vc = _rand_vec(Ah.n, np.complex128)
+    outc = np.zeros(Ah.n, np.complex128)
+    sp.DiagPrecond.new(dreal, dtype=np.complex128).mul_vec(vc, outc)  # DiagPrecond<Complex64,f64>
+    assert np.array_equal(outc, orc.diag_apply(dreal, vc))
+    Ac, _, dc, _ = fx.complex_symmetric_grid(8, 8)
+    sp.DiagPrecond.new(dc).mul_vec(vc, outc)
+    assert np.array_equal(outc, orc.diag_apply(dc, vc))
+
+
+@pytest.mark.parametrize("symmetric", [False, True])
+def test_gauss_seidel_sweep_bit_exact(sp, orc, symmetric):
+    """Level-scheduled sweep == sequential sweep (src/gauss_seidel.rs:111-125), bit for bit."""
+    for A in (orc.gen_lap3d7(12, 11, 10, shift=0.05), orc.gen_convdiff27(9, 8, 7), orc.gen_lap3d7(7, 6, 5, shift=0.5 + 0.5j, dtype=np.complex128)):
+        G = to_gpu(sp, A)
+        P = sp.GaussSeidelPrecond(G, symmetric=symmetric)
+        v = _rand_vec(A.n, A.dtype)
+        out = np.zeros(A.n, A.dtype)
+        P.mul_vec(v, out)
+        assert np.array_equal(out, orc.gs_apply(A, v, symmetric))
+    nf, nb = sp.GaussSeidelPrecond(to_gpu(sp, orc.gen_lap3d7(8, 8, 8)), True).levels()
+    assert nf == nb == 3 * 7 + 1  # hyperplanes i+j+k
+    with pytest.raises(sp.ZeorDiagonalElem) as e:  # src/gauss_seidel.rs:72-78
+        sp.GaussSeidelPrecond(to_gpu(sp, fx.kat_csr()))
+    assert e.value.row == 0
+
+
+# ------------------------------------------------------------------ solvers vs oracle
+def _solve_both(sp, orc, A, rhs, solver, tol, max_iter, pc=None, x0=None):
+    G = to_gpu(sp, A)
+    cls = {"bicgstab": sp.BiCGStab, "minres": sp.MinRes, "csminres": sp.CSMinRes}[solver]
+    S = cls(G, A.n).record_history(max_iter + 1)
+    x = np.zeros(A.n, A.dtype) if x0 is None else x0.astype(A.dtype).copy()
+    P = None
+    if pc is not None:
+        if pc[0] == "diag":
+            P = sp.DiagPrecond.new(pc[1], dtype=A.dtype)
+        else:
+            P = sp.GaussSeidelPrecond(G, symmetric=pc[0] == "gs_sym")
+    if P is None:
+        it, res = S.solve(rhs, x, max_iter, tol)
+    else:
+        it, res = S.precond_solve(P, rhs, x, max_iter, tol)
+    kw = dict(max_iter=max_iter, tol=tol, x0=x0, hist_cap=max_iter + 1)
+    o = getattr(orc, solver)(A, rhs, **kw) if solver == "csminres" else getattr(orc, solver)(A, rhs, pc=pc, **kw)
+    assert o.status == orc.OK
+    return (it, res, x, S.history), o
+
+
+def _check_solve(g, o, tol, A, rhs):
+    it, res, x, hist = g
+    assert_hist(hist, o.hist)
+    assert_iters(it, o.iters)
+    assert res <= tol or res < 2 * tol
+    scale = max(np.abs(o.x).max(), 1.0)
+    assert np.abs(x - o.x).max() <= 50 * tol * scale * max(1.0, np.linalg.norm(rhs) / np.abs(rhs).max()) or np.allclose(x, o.x, rtol=1e-6, atol=1e-8 * scale)
+    true_rel = np.linalg.norm(A.to_scipy() @ x - rhs) / np.linalg.norm(rhs)
+    assert true_rel <= 20 * tol
+
+
+def test_bicgstab_config1_small(sp, orc):
+    """Config C1 at 96^2: reference Dirichlet generator, Jacobi, rtol 1e-8."""
+    A, rhs = orc.gen_dirichlet2d(96)
+    g, o = _solve_both(sp, orc, A, rhs, "bicgstab", 1e-8, 5000, pc=("diag", A.diagonal()))
+    _check_solve(g, o, 1e-8, A, rhs)
+    g, o = _solve_both(sp, orc, A, rhs, "bicgstab", 1e-8, 5000)  # BiCGStab::solve
+    _check_solve(g, o, 1e-8, A, rhs)
+
+
+def test_bicgstab_reference_fixture(sp, orc):
+    """tests/test_solvers.rs:34-57 (20x20, tol 1e-17, 1500 its must converge)."""
+    A, rhs = orc.gen_dirichlet2d(20)
+    G = to_gpu(sp, A)
+    x = np.zeros(A.n)
+    it, res = sp.BiCGStab(G, G.size()).solve(rhs, x, 1500, 1e-17)
+    assert res <= 1e-17
+    ii, jj = np.meshgrid(np.arange(20), np.arange(20), indexing="ij")
+    assert np.allclose(x, (ii + jj).ravel(), atol=1e-11)
+
+
+def test_bicgstab_convdiff27_config5_small(sp, orc):
+    A = orc.gen_convdiff27(20, 18, 16)
+    rhs = orc.spmv(A, np.ones(A.n))
+    g, o = _solve_both(sp, orc, A, rhs, "bicgstab", 1e-8, 500, pc=("diag", A.diagonal()))
+    _check_solve(g, o, 1e-8, A, rhs)
+    assert np.allclose(g[2], 1.0, atol=1e-6)
+    g, o = _solve_both(sp, orc, A, rhs, "bicgstab", 1e-8, 500, pc=("gs_fwd",))  # GS as preconditioner
+    _check_solve(g, o, 1e-8, A, rhs)
+
+
+def test_bicgstab_complex_fixtures(sp, orc):
+    """tests/test_complex_solve.rs:65-88 and tests/test_complex_solve2.rs:5-28 (known x*)."""
+    A, rhs, dreal, xs = fx.hermitian_grid(8, 8)
+    g, o = _solve_both(sp, orc, A, rhs, "bicgstab", 1e-12, 300, pc=("diag", dreal))
+    _check_solve(g, o, 1e-12, A, rhs)
+    assert np.abs(g[2] - xs).max() < 1e-9
+    A, rhs, dc, xs = fx.complex_symmetric_grid(8, 8)
+    g, o = _solve_both(sp, orc, A, rhs, "bicgstab", 1e-12, 300, pc=("diag", dc))
+    _check_solve(g, o, 1e-12, A, rhs)
+    assert np.abs(g[2] - xs).max() < 1e-9
+    x = np.zeros(A.n, np.complex128)  # the reference's own tolerance (1e-22) must converge too
+    G = to_gpu(sp, A)
+    sp.BiCGStab(G, A.n).precond_solve(sp.DiagPrecond.new(dc), rhs, x, 300, 1e-22)
+    assert np.abs(x - xs).max() < 1e-12
+
+
+def test_minres_fixtures(sp, orc):
+    """tests/test_minres.rs:2-60, tests/test_complex_solve.rs:4-62."""
+    A, rhs = fx.sym_laplacian_2d(8, 8)
+    g, o = _solve_both(sp, orc, A, rhs, "minres", 1e-12, 300)
+    _check_solve(g, o, 1e-12, A, rhs)
+    A, rhs = fx.diag_simple(8, 8)
+    g, o = _solve_both(sp, orc, A, rhs, "minres", 1e-12, 300)
+    assert np.allclose(g[2], 0.5, atol=1e-10)
+    A, rhs, dreal, xs = fx.hermitian_grid(8, 8)
+    g, o = _solve_both(sp, orc, A, rhs, "minres", 1e-12, 300)
+    _check_solve(g, o, 1e-12, A, rhs)
+    g, o = _solve_both(sp, orc, A, rhs, "minres", 1e-12, 300, pc=("diag", dreal))
+    _check_solve(g, o, 1e-12, A, rhs)
+    assert np.abs(g[2] - xs).max() < 1e-8
+
+
+def test_minres_sgs_config3_small(sp, orc):
+    """Config C3 at 20^3: shifted (indefinite) 7-point Laplacian, SGS preconditioner."""
+    A = orc.gen_lap3d7(20, shift=0.05)
+    rhs = orc.spmv(A, np.ones(A.n))
+    g, o = _solve_both(sp, orc, A, rhs, "minres", 1e-8, 400, pc=("gs_sym",))
+    _check_solve(g, o, 1e-8, A, rhs)
+    g, o = _solve_both(sp, orc, A, rhs, "minres", 1e-8, 400)
+    _check_solve(g, o, 1e-8, A, rhs)
+
+
+def test_csminres_config4_small(sp, orc):
+    """Config C4 at 20^3: complex-symmetric Helmholtz, CSMinRes (parity unpinned by the
+    reference, checked against the oracle and the known solution)."""
+    A = orc.gen_lap3d7(20, shift=0.5 + 0.5j, dtype=np.complex128)
+    xs = np.full(A.n, 1 + 1j)
+    rhs = orc.spmv(A, xs)
+    g, o = _solve_both(sp, orc, A, rhs, "csminres", 1e-8, 600)
+    _check_solve(g, o, 1e-8, A, rhs)
+    assert np.abs(g[2] - xs).max() < 1e-5
+    A, rhs, _, xs = fx.complex_symmetric_grid(8, 8)
+    g, o = _solve_both(sp, orc, A, rhs, "csminres", 1e-12, 300)
+    _check_solve(g, o, 1e-12, A, rhs)
+    assert np.abs(g[2] - xs).max() < 1e-8
+
+
+def test_gauss_seidel_solver(sp, orc):
+    """tests/test_solvers.rs:3-31 (10x10, 300 sweeps, eps 0) + history parity."""
+    A, rhs = orc.gen_dirichlet2d(10)
+    G = to_gpu(sp, A)
+    S = sp.GaussSeidel(G).record_history(300)
+    x = np.zeros(A.n)
+    it, res = S.solve(rhs, x, 300, 0.0)
+    o = orc.gauss_seidel(A, rhs, max_iter=300, eps=0.0)
+    assert (it, res) == (o.iters, o.resid) and np.array_equal(x, o.x)
+    k = min(len(S.history), len(o.hist))
+    assert np.allclose(S.history[:k], o.hist[:k], rtol=1e-9, atol=1e-300)
+    A = orc.gen_convdiff27(8, 8, 8)
+    rhs = orc.spmv(A, np.ones(A.n))
+    x = np.zeros(A.n)
+    it, res = sp.GaussSeidel(to_gpu(sp, A)).solve(rhs, x, 200, 1e-9)
+    o = orc.gauss_seidel(A, rhs, max_iter=200, eps=1e-9)
+    assert it == o.iters and np.array_equal(x, o.x)
+    with pytest.raises(sp.InsufficientIterNum):
+        sp.GaussSeidel(G).solve(rhs[: G.size()], np.zeros(G.size()), 0, 0.0)  # src/gauss_seidel.rs:52-54
+    with pytest.raises(sp.ZeorDiagonalElem):
+        sp.GaussSeidel(to_gpu(sp, fx.kat_csr())).solve(np.ones(5), np.zeros(5), 5, 0.0)
+
+
+def test_solver_semantics(sp, orc):
+    """SURVEY.md section 9 cheat-sheet, through the C ABI."""
+    A, rhs = orc.gen_dirichlet2d(12)
+    G = to_gpu(sp, A)
+    for cls in (sp.BiCGStab, sp.MinRes, sp.CSMinRes):
+        x = np.ones(A.n)
+        assert cls(G, A.n).solve(np.zeros(A.n), x, 10, 1e-8) == (0, 0.0) and np.all(x == 0)  # zero rhs
+        with pytest.raises(sp.IncompatibleMatrixFormat):
+            cls(G, A.n).solve(rhs[:-1], np.zeros(A.n - 1), 10, 1e-8)
+        with pytest.raises(sp.IncompatibleMatrixFormat):
+            cls(G, A.n).solve(rhs, np.zeros(A.n - 1), 10, 1e-8)
+    full = orc.bicgstab(A, rhs, max_iter=1000, tol=1e-8)
+    S = sp.BiCGStab(G, A.n)
+    with pytest.raises(sp.InsufficientIterNum) as e:  # check sits at the top of the NEXT iteration
+        S.solve(rhs, np.zeros(A.n), full.iters, 1e-8)
+    assert e.value.max_iter == full.iters
+    x = np.zeros(A.n)
+    assert S.solve(rhs, x, full.iters + 1, 1e-8)[0] == full.iters  # workspace is reusable
+    for poll in (1, 3, 64):  # host polling cadence must not change the result
+        x2 = np.zeros(A.n)
+        S.set_poll_interval(poll)
+        assert S.solve(rhs, x2, 1000, 1e-8)[0] == full.iters and np.array_equal(x2, x)
+    As, rs = fx.sym_laplacian_2d(6, 6)
+    Gs = to_gpu(sp, As)
+    with pytest.raises(sp.InvalidPreconditioner):  # negative definite M, src/minres.rs:236-244
+        sp.MinRes(Gs, As.n).precond_solve(sp.DiagPrecond.new(As.diagonal()), rs, np.zeros(As.n), 50, 1e-10)
+    # warm start: x is in/out
+    xw = full.x.copy()
+    assert sp.BiCGStab(G, A.n).solve(rhs, xw, 50, 1e-6)[0] == 0
+
+
+def test_bicgstab_restart_path(sp, orc):
+    """Exercise the rho-restart branch (src/bicg_stab.rs:304-318) on both sides: a tolerance no
+    residual can reach makes rho underflow the restart threshold long before max_iter."""
+    A = orc.gen_lap3d7(6, shift=0.0)
+    rhs = orc.spmv(A, np.ones(A.n))
+    o = orc.bicgstab(A, rhs, max_iter=400, tol=1e-30, hist_cap=401)
+    G = to_gpu(sp, A)
+    S = sp.BiCGStab(G, A.n).record_history(401)
+    x = np.zeros(A.n)
+    try:
+        it, res = S.solve(rhs, x, 400, 1e-30)
+        st = orc.OK
+    except sp.InsufficientIterNum:
+        st = orc.INSUFFICIENT_ITER
+    except sp.BreakDown:
+        st = orc.BREAKDOWN
+    assert st == o.status
+    assert_hist(S.history, o.hist, k=30)
+    assert np.isfinite(x).all() == np.isfinite(o.x).all()
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_spmv_config2_full_size_properties(sp):
+    """Config C2 (256^3 7-point): size-independent properties instead of an oracle run:
+    A*1 = row sums, linearity, and sum(A x) = (A^T 1) . x = (A 1) . x for the symmetric stencil."""
+    import torch
+
+    n1 = 256
+    n = n1**3
+    G = sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, n1, n1, n1, params=(0.0,))
+    assert G.nnz == 7 * n - 6 * n1 * n1 == 117047296
+    dev = torch.device("cuda:0")
+    ones = torch.ones(n, dtype=torch.float64, device=dev)
+    k = torch.arange(n, device=dev)
+    x = 1.0 + (k % 17).double() / 17.0
+    z = torch.cos(k.double() * 1e-3)
+    ya, yx, yz, yc = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(4))
+    torch.cuda.synchronize()
+    G.mul_vec_dev(ones.data_ptr(), ya.data_ptr())
+    G.mul_vec_dev(x.data_ptr(), yx.data_ptr())
+    G.mul_vec_dev(z.data_ptr(), yz.data_ptr())
+    comb = 0.75 * x - 1.25 * z
+    G.mul_vec_dev(comb.data_ptr(), yc.data_ptr())
+    G.ctx.synchronize()
+    g = ya.view(n1, n1, n1)
+    assert float(g[1:-1, 1:-1, 1:-1].abs().max()) == 0.0  # interior rows sum to 6 - 6
+    assert float(g[0, 0, 0]) == 3.0 and float(g[0, 5, 5]) == 1.0
+    assert torch.allclose(yc, 0.75 * yx - 1.25 * yz, rtol=0, atol=1e-12)
+    assert abs(float(yx.sum()) - float((ya * x).sum())) <= 1e-9 * float(yx.abs().sum())
