@@ -171,10 +171,22 @@ spmv_tile_kernel(const SpmvArgs<T, IP> a) {
       }
       __syncthreads();
     } else {
-      // ---- tile holds a row longer than the staging buffer: the whole CTA strides over each
-      //      row.  (Summation order differs from the reference for such rows only.)
+      // ---- the tile holds a row longer than the staging buffer (rare).  Rows up to TILE/2
+      //      non-zeros keep the sequential thread-per-row fold, read straight from global
+      //      memory; longer rows are strided over by the whole CTA (their summation order
+      //      differs from the reference).
+      for (int r = r0 + tid; r < r1; r += THREADS) {
+        const IP p0 = a.indptr[r], p1 = a.indptr[r + 1];
+        if (p1 - p0 > (IP)(TILE / 2)) continue;
+        T acc = zero_of<T>();
+        for (IP k = p0; k < p1; ++k)
+          acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k]), a.vals[k]));
+        a.y[r] = acc;
+        epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+      }
       for (int r = r0; r < r1; ++r) {
         const IP p0 = a.indptr[r], p1 = a.indptr[r + 1];
+        if (p1 - p0 <= (IP)(TILE / 2)) continue;
         T acc = zero_of<T>();
         for (IP k = p0 + tid; k < p1; k += THREADS)
           acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k]), a.vals[k]));
