@@ -93,7 +93,11 @@ int spb_csr_create(spb_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_
 /* Generates the matrix on the device (this rank's row block when a communicator is set). */
 int spb_csr_create_stencil(spb_ctx* ctx, int kind, int dtype, int64_t nx, int64_t ny, int64_t nz,
                            const double* params, int nparams, spb_op** out);
-/* MklMat::mv_hint / mv_and_dotmv_hint (src/mkl_mat.rs:81-148): re-run the analysis. */
+/* MklMat::mv_hint / mv_and_dotmv_hint (src/mkl_mat.rs:81-148), i.e. mkl_sparse_set_mv_hint +
+ * mkl_sparse_optimize: time a handful of launch plans with real SpMV launches on this matrix and
+ * keep the fastest.  Optional: spb_csr_create already picks a static plan.  The plan fixes the
+ * summation order of the fused dot products, so call it before the first solve if at all.
+ * Collective when the matrix is partitioned (every rank must call it). */
 int spb_csr_mv_hint(spb_op* mat, int ncalls);
 int spb_csr_mv_and_dotmv_hint(spb_op* mat, int ncalls);
 /* MklMat::size (src/mkl_mat.rs:26-28), plus local sizes for partitioned matrices. */

@@ -252,9 +252,9 @@ static int rehint(spb_op* m) {
   SPB_REQUIRE(m && m->kind == OP_CSR, "not a CSR matrix");
   use_device(m->ctx);
   if (m->dtype == SPB_F64)
-    static_cast<CsrMat<double>*>(m)->analyze();
+    static_cast<CsrMat<double>*>(m)->autotune();
   else
-    static_cast<CsrMat<cplx>*>(m)->analyze();
+    static_cast<CsrMat<cplx>*>(m)->autotune();
   return SPB_OK;
   SPB_CATCH
 }

@@ -30,7 +30,12 @@ struct CsrMat : spb_op {
   int64_t max_row = 0;
 
   // --- analysis (the mkl_sparse_optimize analogue): nnz-balanced row tiles -----------------
-  int cfg = 0;           // kernel configuration (threads, tile)
+  int plan_ct = 128;     // consumer threads per CTA (one row per thread and tile)
+  int plan_stages = 2;   // shared-memory stages of the bulk-copy ring
+  int plan_gb = 0;       // 1: x gathered with cp.async into shared memory, 0: into registers
+  int plan_tile = 2048;  // non-zeros staged per tile
+  int plan_rcap = 264;   // indptr entries staged per tile
+  int plan_bps = 1;      // resident CTAs per SM (occupancy)
   int64_t span = 0;      // tile t = rows whose first nnz lies in [t*span, (t+1)*span)
   int64_t ntiles = 0;
   DevBuf tile_row;       // int32 [ntiles+1]
@@ -51,6 +56,8 @@ struct CsrMat : spb_op {
   DevBuf stage_in, stage_out;
 
   void analyze();
+  void build_plan(int consumer_threads, int stages);
+  void autotune();
   // y = A x (x, y device pointers to LOCAL vectors).  conj_in: multiply by conj(x) (CSMinRes,
   // src/cs_minres.rs:99-101, without materialising tvec).  Epilogue sums land in `red` after
   // finalize_epilogue() (local sum only; the caller all-reduces when distributed).

@@ -9,11 +9,15 @@
 //     whatever the row lengths are;
 //   * a persistent grid (a multiple of the SM count) walks the tiles round-robin, so concurrently
 //     running CTAs work on neighbouring rows and the x window they gather from stays in L2;
-//   * per tile, col_idx / values are streamed with coalesced 128-bit ld.global.nc.L1::no_allocate
-//     loads into shared memory (the matrix is read exactly once and never pollutes L1);
-//   * then one thread per row accumulates  acc = acc + x[col] * val  SEQUENTIALLY IN CSR ORDER --
-//     the same left fold as src/mat.rs:100-105 -- so y is bit-identical to the reference; lanes of
-//     a warp walk the same stencil diagonal, so the x gathers (ld.global.nc through L1) coalesce;
+//   * per tile, one producer lane streams col_idx / values / the indptr slice into a ring of
+//     shared-memory stages with 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx: the
+//     TMA engine, UBLKCP in SASS) -- the matrix is read exactly once, never touches L1 or
+//     registers, and the next tiles are in flight while the current one is being reduced;
+//   * the consumer warps run one thread per row accumulating  acc = acc + x[col] * val
+//     SEQUENTIALLY IN CSR ORDER -- the same left fold as src/mat.rs:100-105 -- so y is
+//     bit-identical to the reference; lanes of a warp walk the same stencil diagonal, so the x
+//     gathers coalesce; they are issued as asynchronous global->shared copies (cp.async,
+//     LDGSTS, through L1), so every gather of a row is in flight at once whatever its length;
 //   * dot-product epilogues (<r0,v>, <t,t>, <t,r>, conj(x).y) are folded in, so the Krylov loops
 //     never re-read the SpMV output for a reduction.
 // Algorithmic bytes per launch: nnz*(sizeof(T)+4) + (n+1)*sizeof(indptr) + 2*n*sizeof(T).
@@ -24,59 +28,31 @@
 
 namespace spb {
 
-// ---------------------------------------------------------------- streaming loads
-__device__ __forceinline__ int4 ld_stream_int4(const int* p) {
-  int4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
+// ---------------------------------------------------------------- x gathers (read-only path, L1)
+// L2 residency control: the matrix is streamed exactly once (evict_first), every x entry is
+// gathered nnz-per-column times over a window of a few grid planes (evict_last).  Without the
+// hints the 12 bytes/nnz matrix stream pushes x out of the 126 MB L2 before the next plane reuses
+// it (27-point 512^3: one plane of rows streams 91 MB of matrix) and the gathers pay HBM latency.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
-__device__ __forceinline__ double2 ld_stream_double2(const double* p) {
-  double2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
-               : "=d"(r.x), "=d"(r.y)
-               : "l"(p));
-  return r;
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
-__device__ __forceinline__ double ld_x(const double* p) { return __ldg(p); }
-__device__ __forceinline__ cplx ld_x(const cplx* p) {
-  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
-  return cplx{v.x, v.y};
+__device__ __forceinline__ double ld_x(const double* p, uint64_t pol) {
+  double v;
+  asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
 }
-
-template <typename T>
-struct ValPack;  // 4 consecutive values staged by one thread
-template <>
-struct ValPack<double> {
-  double2 a, b;
-  __device__ __forceinline__ void load(const double* p) {
-    a = ld_stream_double2(p);
-    b = ld_stream_double2(p + 2);
-  }
-  __device__ __forceinline__ void store(double* s) const {
-    *reinterpret_cast<double2*>(s) = a;
-    *reinterpret_cast<double2*>(s + 2) = b;
-  }
-};
-template <>
-struct ValPack<cplx> {
-  double2 a, b, c, d;
-  __device__ __forceinline__ void load(const cplx* p) {
-    const double* q = reinterpret_cast<const double*>(p);
-    a = ld_stream_double2(q);
-    b = ld_stream_double2(q + 2);
-    c = ld_stream_double2(q + 4);
-    d = ld_stream_double2(q + 6);
-  }
-  __device__ __forceinline__ void store(cplx* s) const {
-    double2* q = reinterpret_cast<double2*>(s);
-    q[0] = a;
-    q[1] = b;
-    q[2] = c;
-    q[3] = d;
-  }
-};
+__device__ __forceinline__ cplx ld_x(const cplx* p, uint64_t pol) {
+  cplx v;
+  asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.re), "=d"(v.im) : "l"(p), "l"(pol));
+  return v;
+}
 
 template <typename T, typename IP>
 struct SpmvArgs {
@@ -94,11 +70,17 @@ struct SpmvArgs {
   T* partials;   // [2 * gridDim.x]
   const int* gate;  // optional solver gate (see Ctx::gate)
   int gate_value;
+  int tile;      // staging capacity in non-zeros (multiple of 4)
+  int rcap;      // staging capacity in indptr entries
+  int stages;
 };
 
 template <typename T, bool CONJ_IN>
-__device__ __forceinline__ T gather_x(const T* x, const T* xh, int n_local, int c) {
-  T v = (c < n_local) ? ld_x(x + c) : ld_x(xh + (c - n_local));
+__device__ __forceinline__ T gather_x(const T* x, const T* xh, int n_local, int c, uint64_t pol) {
+  // one unconditional load through a selected pointer: a branch around the load would make
+  // ptxas wait for each gather before issuing the next one
+  const T* p = (c < n_local) ? (x + c) : (xh + (c - n_local));
+  T v = ld_x(p, pol);
   if (CONJ_IN) v = conj_of(v);
   return v;
 }
@@ -114,87 +96,266 @@ __device__ __forceinline__ void epilogue_acc(T acc, const T* w, int64_t r, T& e0
   }
 }
 
-template <typename T, typename IP, int THREADS, int TILE, int EPI, bool CONJ_IN>
-__global__ void __launch_bounds__(THREADS)
-spmv_tile_kernel(const SpmvArgs<T, IP> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* s_val = reinterpret_cast<T*>(smem_raw);
-  int* s_col = reinterpret_cast<int*>(s_val + (TILE + 4));
-  T* s_red = reinterpret_cast<T*>(s_col + (TILE + 4));  // 32 T
+// ---------------------------------------------------------------- mbarrier / bulk-copy PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync(int nthreads) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
-  constexpr int ITERS = TILE / (THREADS * 4) + 1;  // +1: up to 3 head elements before the tile
-  const int tid = threadIdx.x;
-  T e0 = zero_of<T>(), e1 = zero_of<T>();
+__device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(cplx* smem_dst, const cplx* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
+}
+
+struct TileMeta {
+  int r0, r1;     // rows of the tile
+  int total;      // staged non-zeros counted from the 4-aligned base; -1 => long-row tile
+  int ip_off;     // index of indptr[r0] inside the staged indptr slice; -1 => slice not staged
+  long long s4;   // 4-aligned first non-zero
+};
+
+__host__ __device__ inline int align16i(int v) { return (v + 15) & ~15; }
+
+// Sum over the consumer threads only (named barrier 1); result valid in consumer thread 0.
+template <typename T>
+__device__ __forceinline__ T consumer_sum(T v, T* scratch, int nthreads) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) scratch[wid] = v;
+  consumer_bar_sync(nthreads);
+  T tot = zero_of<T>();
+  if (threadIdx.x == 0)
+    for (int w = 0; w < nthreads / 32; ++w) tot = add(tot, scratch[w]);
+  consumer_bar_sync(nthreads);
+  return tot;
+}
+
+static const int kMaxStages = 4;
+
+template <typename T, typename IP>
+__device__ __forceinline__ void row_range(const SpmvArgs<T, IP>& a, const TileMeta& m, const IP* s_ip, int r,
+                                          int& p0, int& p1) {
+  if (m.ip_off >= 0) {
+    const int q = m.ip_off + (r - m.r0);
+    p0 = (int)((long long)s_ip[q] - m.s4);
+    p1 = (int)((long long)s_ip[q + 1] - m.s4);
+  } else {
+    p0 = (int)((long long)a.indptr[r] - m.s4);
+    p1 = (int)((long long)a.indptr[r + 1] - m.s4);
+  }
+}
+
+// blockDim.x = CT consumer threads + one producer warp.
+template <typename T, typename IP, bool AX, int EPI, bool CONJ_IN>
+__global__ void __launch_bounds__(288)
+spmv_tma_kernel(const SpmvArgs<T, IP> a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int CT = (int)blockDim.x - 32;
+  const int VAL_BYTES = align16i((a.tile + 4) * (int)sizeof(T));
+  const int COL_BYTES = align16i((a.tile + 4) * 4);
+  const int IP_BYTES = align16i((a.rcap + 8) * (int)sizeof(IP));
+  const int STAGE_BYTES = (AX ? 2 : 1) * VAL_BYTES + COL_BYTES + IP_BYTES;  // vals | cols | indptr slice | [gathered x]
+  const int STAGES = a.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + kMaxStages;
+  TileMeta* meta = reinterpret_cast<TileMeta*>(empty + kMaxStages);
+  T* s_red = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(meta + kMaxStages) + 15) & ~(uintptr_t)15);
+
   if (a.gate && *a.gate != a.gate_value) return;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], CT / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
 
-  for (int64_t ti = blockIdx.x; ti < a.ntiles; ti += gridDim.x) {
-    const int tile = a.tile_list ? a.tile_list[ti] : (int)ti;
-    const int r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
-    const IP s = a.indptr[r0], e = a.indptr[r1];
-    const int64_t cnt = (int64_t)(e - s);
-    if (cnt <= TILE) {
-      // ---- stage cols / vals: aligned 128-bit streaming loads, all issued before any store
-      const IP s4 = s & ~(IP)3;
-      const int total = (int)(e - s4);
-      const int* gc = a.cols + s4;
-      const T* gv = a.vals + s4;
-      int4 c4[ITERS];
-      ValPack<T> v4[ITERS];
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int j = (it * THREADS + tid) * 4;
-        if (j < total) {
-          c4[it] = ld_stream_int4(gc + j);
-          v4[it].load(gv + j);
+  const int64_t my_tiles = a.ntiles > (int64_t)blockIdx.x
+                               ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x
+                               : 0;
+  T e0 = zero_of<T>(), e1 = zero_of<T>();
+
+  if (tid >= CT) {
+    // ------------------------------------------------------------ producer (one lane)
+    if (tid == CT) {
+      constexpr int IPV = 16 / (int)sizeof(IP);  // indptr entries per 16 bytes
+      const uint64_t pol_stream = l2_policy_evict_first();
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t i = 0; i < my_tiles; ++i) {
+        const int64_t ti = blockIdx.x + i * gridDim.x;
+        const int tile = a.tile_list ? a.tile_list[ti] : (int)ti;
+        const int r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
+        const IP st = a.indptr[r0], en = a.indptr[r1];
+        const IP s4 = st & ~(IP)3;
+        mbar_wait(&empty[s], ph ^ 1u);  // stage released by every consumer warp
+        TileMeta m;
+        m.r0 = r0;
+        m.r1 = r1;
+        m.s4 = (long long)s4;
+        unsigned char* stage = smem_raw + s * STAGE_BYTES;
+        if ((int64_t)(en - st) <= a.tile) {
+          m.total = (int)(en - s4);
+          const int ra = r0 & ~(IPV - 1);  // 16-byte aligned start of the indptr slice
+          const int nip = ((r1 + 1 - ra) + IPV - 1) & ~(IPV - 1);
+          const bool ip_ok = nip <= a.rcap + 8 - IPV;
+          m.ip_off = ip_ok ? (r0 - ra) : -1;
+          meta[s] = m;
+          const uint32_t groups = (uint32_t)((m.total + 3) >> 2);
+          const uint32_t bytes = groups * (16u + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u);
+          if (bytes) {
+            mbar_arrive_expect_tx(&full[s], bytes);
+            if (groups) {
+              bulk_g2s(stage, a.vals + s4, groups * 4u * (uint32_t)sizeof(T), &full[s], pol_stream);
+              bulk_g2s(stage + VAL_BYTES, a.cols + s4, groups * 16u, &full[s], pol_stream);
+            }
+            if (ip_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES, a.indptr + ra, (uint32_t)nip * (uint32_t)sizeof(IP), &full[s], pol_stream);
+          } else {
+            mbar_arrive(&full[s]);
+          }
+        } else {
+          m.total = -1;  // long-row tile: consumers read it from global memory
+          m.ip_off = -1;
+          meta[s] = m;
+          mbar_arrive(&full[s]);
+        }
+        if (++s == STAGES) {
+          s = 0;
+          ph ^= 1u;
         }
       }
-#pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int j = (it * THREADS + tid) * 4;
-        if (j < total) {
-          *reinterpret_cast<int4*>(s_col + j) = c4[it];
-          v4[it].store(s_val + j);
+    }
+  } else {
+    // ------------------------------------------------------------ consumers
+    const uint64_t pol_x = l2_policy_evict_last();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      mbar_wait(&full[s], ph);
+      const TileMeta m = meta[s];
+      const unsigned char* stage = smem_raw + s * STAGE_BYTES;
+      const T* s_val = reinterpret_cast<const T*>(stage);
+      const int* s_col = reinterpret_cast<const int*>(stage + VAL_BYTES);
+      const IP* s_ip = reinterpret_cast<const IP*>(stage + VAL_BYTES + COL_BYTES);
+      T* s_x = reinterpret_cast<T*>(smem_raw + s * STAGE_BYTES + VAL_BYTES + COL_BYTES + IP_BYTES);
+      (void)s_x;
+      if (m.total >= 0 && AX) {
+        // phase A: every x entry this thread's rows need is fetched with an asynchronous
+        // global->shared copy (cp.async, LDGSTS): no register result, so all gathers of the
+        // row(s) are in flight at once whatever the row length.  Lanes of a warp walk the same
+        // stencil diagonal, so each LDGSTS is a coalesced 256-byte request through L1.
+        for (int r = m.r0 + tid; r < m.r1; r += CT) {
+          int p0, p1;
+          row_range(a, m, s_ip, r, p0, p1);
+          for (int k = p0; k < p1; ++k) {
+            const int c = s_col[k];
+            const T* src = (c < a.n_local) ? (a.x + c) : (a.xh + (c - a.n_local));
+            cp_async_elem(s_x + k, src);
+          }
         }
-      }
-      __syncthreads();
-      // ---- one thread per row, sequential fold in CSR order (src/mat.rs:100-105)
-      for (int r = r0 + tid; r < r1; r += THREADS) {
-        const int p0 = (int)(a.indptr[r] - s4), p1 = (int)(a.indptr[r + 1] - s4);
-        T acc = zero_of<T>();
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        // phase B: sequential fold in CSR order out of shared memory (src/mat.rs:100-105);
+        // each thread reads only what it gathered itself, so no CTA barrier is needed.
+        for (int r = m.r0 + tid; r < m.r1; r += CT) {
+          int p0, p1;
+          row_range(a, m, s_ip, r, p0, p1);
+          T acc = zero_of<T>();
 #pragma unroll 4
-        for (int k = p0; k < p1; ++k) {
-          const T xv = gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, s_col[k]);
-          acc = add(acc, mul(xv, s_val[k]));
-        }
-        a.y[r] = acc;
-        epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
-      }
-      __syncthreads();
-    } else {
-      // ---- the tile holds a row longer than the staging buffer (rare).  Rows up to TILE/2
-      //      non-zeros keep the sequential thread-per-row fold, read straight from global
-      //      memory; longer rows are strided over by the whole CTA (their summation order
-      //      differs from the reference).
-      for (int r = r0 + tid; r < r1; r += THREADS) {
-        const IP p0 = a.indptr[r], p1 = a.indptr[r + 1];
-        if (p1 - p0 > (IP)(TILE / 2)) continue;
-        T acc = zero_of<T>();
-        for (IP k = p0; k < p1; ++k)
-          acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k]), a.vals[k]));
-        a.y[r] = acc;
-        epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
-      }
-      for (int r = r0; r < r1; ++r) {
-        const IP p0 = a.indptr[r], p1 = a.indptr[r + 1];
-        if (p1 - p0 <= (IP)(TILE / 2)) continue;
-        T acc = zero_of<T>();
-        for (IP k = p0 + tid; k < p1; k += THREADS)
-          acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k]), a.vals[k]));
-        acc = block_sum(acc, s_red);
-        if (tid == 0) {
+          for (int k = p0; k < p1; ++k) {
+            T xv = s_x[k];
+            if (CONJ_IN) xv = conj_of(xv);
+            acc = add(acc, mul(xv, s_val[k]));
+          }
           a.y[r] = acc;
           epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
         }
+      } else if (m.total >= 0) {
+        // register gathers (ld.global.nc through L1), 8 per batch, sequential fold in CSR order
+        for (int r = m.r0 + tid; r < m.r1; r += CT) {
+          int p0, p1;
+          row_range(a, m, s_ip, r, p0, p1);
+          T acc = zero_of<T>();
+          for (int k = p0; k < p1; k += 8) {
+            int c[8];
+            T xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = s_col[min(k + j, p1 - 1)];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, c[j], pol_x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (k + j < p1) acc = add(acc, mul(xv[j], s_val[k + j]));  // src/mat.rs:100-105
+          }
+          a.y[r] = acc;
+          epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+        }
+      } else {
+        // rows up to tile/2 non-zeros keep the sequential fold (read from global memory);
+        // longer rows are strided over by all consumers (their summation order differs).
+        for (int r = m.r0 + tid; r < m.r1; r += CT) {
+          const IP p0 = a.indptr[r], p1 = a.indptr[r + 1];
+          if (p1 - p0 > (IP)(a.tile / 2)) continue;
+          T acc = zero_of<T>();
+          for (IP k = p0; k < p1; ++k)
+            acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k], pol_x), a.vals[k]));
+          a.y[r] = acc;
+          epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+        }
+        for (int r = m.r0; r < m.r1; ++r) {
+          const IP p0 = a.indptr[r], p1 = a.indptr[r + 1];
+          if (p1 - p0 <= (IP)(a.tile / 2)) continue;
+          T acc = zero_of<T>();
+          for (IP k = p0 + tid; k < p1; k += CT)
+            acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k], pol_x), a.vals[k]));
+          acc = consumer_sum(acc, s_red, CT);
+          if (tid == 0) {
+            a.y[r] = acc;
+            epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+          }
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&empty[s]);  // this warp is done with stage s
+      if (++s == STAGES) {
+        s = 0;
+        ph ^= 1u;
       }
     }
   }
@@ -255,74 +416,60 @@ __global__ void finalize_partials_kernel(const T* partials, int64_t nblocks, sca
   }
 }
 
-// ---------------------------------------------------------------- configuration table
-struct SpmvCfg {
-  int threads, tile;
-};
-static const SpmvCfg kCfgs[] = {{128, 2048}, {256, 4096}, {128, 1024}, {256, 2048}};
-static const int kNumCfgs = 4;
-
-template <typename T>
-static size_t spmv_smem_bytes(int tile) {
-  return (size_t)(tile + 4) * (sizeof(T) + 4) + 32 * sizeof(T);
+// ---------------------------------------------------------------- launch plumbing
+template <typename T, typename IP>
+static size_t spmv_smem_bytes(const CsrMat<T>* m) {
+  const size_t stage = (m->plan_gb ? 2 : 1) * (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + align16i((m->plan_tile + 4) * 4) +
+                       align16i((m->plan_rcap + 8) * (int)sizeof(IP));
+  return m->plan_stages * stage + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(T) + 32;
 }
 
-template <typename T, typename IP, int THREADS, int TILE>
-static void launch_cfg(Ctx* ctx, const SpmvArgs<T, IP>& args, int epi, bool conj_in, int grid) {
-  const size_t smem = spmv_smem_bytes<T>(TILE);
-#define SPB_SPMV_CASE(E, C)                                                                      \
-  {                                                                                              \
-    auto k = spmv_tile_kernel<T, IP, THREADS, TILE, E, C>;                                       \
-    static bool attr_set = false;                                                                \
-    if (!attr_set) {                                                                             \
-      SPB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set = true;                                                                           \
-    }                                                                                            \
-    k<<<grid, THREADS, smem, ctx->stream>>>(args);                                               \
-  }
-  if (!conj_in) {
-    if (epi == EPI_NONE) SPB_SPMV_CASE(EPI_NONE, false)
-    else if (epi == EPI_DOT_WY) SPB_SPMV_CASE(EPI_DOT_WY, false)
-    else SPB_SPMV_CASE(EPI_TT_TR, false)
+// Runs f(kernel_pointer) for the kernel instance selected by (async_x, epi, conj).
+template <typename T, typename IP, bool AX, typename F>
+static void with_kernel_ax(int epi, bool conj_in, F&& f) {
+  constexpr bool CZ = ScalarTraits<T>::is_complex;
+  if (CZ && conj_in) {
+    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, AX, EPI_NONE, CZ>);
+    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, AX, EPI_DOT_WY, CZ>);
+    else f(spmv_tma_kernel<T, IP, AX, EPI_TT_TR, CZ>);
   } else {
-    if (epi == EPI_NONE) SPB_SPMV_CASE(EPI_NONE, true)
-    else if (epi == EPI_DOT_WY) SPB_SPMV_CASE(EPI_DOT_WY, true)
-    else SPB_SPMV_CASE(EPI_TT_TR, true)
+    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, AX, EPI_NONE, false>);
+    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, AX, EPI_DOT_WY, false>);
+    else f(spmv_tma_kernel<T, IP, AX, EPI_TT_TR, false>);
   }
-#undef SPB_SPMV_CASE
-  check_launch("spmv_tile_kernel");
+}
+template <typename T, typename IP, typename F>
+static void with_kernel(int async_x, int epi, bool conj_in, F&& f) {
+  if (async_x) with_kernel_ax<T, IP, true>(epi, conj_in, f);
+  else with_kernel_ax<T, IP, false>(epi, conj_in, f);
 }
 
 template <typename T, typename IP>
-static void launch_spmv(Ctx* ctx, int cfg, const SpmvArgs<T, IP>& args, int epi, bool conj_in,
-                        int grid) {
+static void launch_spmv(CsrMat<T>* m, const SpmvArgs<T, IP>& args, int epi, bool conj_in, int grid) {
+  Ctx* ctx = m->ctx;
   LaunchScope ls(ctx, FAM_SPMV);
-  switch (cfg) {
-    case 0: launch_cfg<T, IP, 128, 2048>(ctx, args, epi, conj_in, grid); break;
-    case 1: launch_cfg<T, IP, 256, 4096>(ctx, args, epi, conj_in, grid); break;
-    case 2: launch_cfg<T, IP, 128, 1024>(ctx, args, epi, conj_in, grid); break;
-    default: launch_cfg<T, IP, 256, 2048>(ctx, args, epi, conj_in, grid); break;
-  }
+  const size_t smem = spmv_smem_bytes<T, IP>(m);
+  with_kernel<T, IP>(m->plan_gb, epi, conj_in, [&](auto kernel) {
+    SPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, m->plan_ct + 32, smem, ctx->stream>>>(args);
+  });
+  check_launch("spmv_tma_kernel");
 }
 
 template <typename T, typename IP>
-static int spmv_blocks_per_sm(int cfg) {
+static int spmv_blocks_per_sm(CsrMat<T>* m) {
   int nb = 0;
-  const size_t smem = spmv_smem_bytes<T>(kCfgs[cfg].tile);
-#define SPB_OCC(TH, TL)                                                                        \
-  {                                                                                            \
-    auto k = spmv_tile_kernel<T, IP, TH, TL, EPI_TT_TR, false>;                                \
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, TH, smem);                           \
-  }
-  switch (cfg) {
-    case 0: SPB_OCC(128, 2048) break;
-    case 1: SPB_OCC(256, 4096) break;
-    case 2: SPB_OCC(128, 1024) break;
-    default: SPB_OCC(256, 2048) break;
-  }
-#undef SPB_OCC
+  const size_t smem = spmv_smem_bytes<T, IP>(m);
+  with_kernel<T, IP>(m->plan_gb, EPI_TT_TR, false, [&](auto kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, m->plan_ct + 32, smem);
+  });
   return nb > 0 ? nb : 1;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
 }
 
 // ---------------------------------------------------------------- CsrMat methods
@@ -349,15 +496,47 @@ void CsrMat<T>::analyze() {
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   max_row = (int64_t)h;
 
-  // configuration: short rows -> small CTAs / small tiles keep ~all threads busy in the row phase
+  // ---- launch plan: a static rule (same plan for the same matrix on every run, so the fused
+  //      dot products are bit-reproducible run to run); env overrides are for tuning sweeps.
+  // One consumer thread per row and tile.  Measured on B200 (profiles/r01_spmv_plan_sweep.txt):
+  // ~21 KB per stage is the sweet spot; rows of <= 12 non-zeros want a 2-stage ring (the row
+  // phase is short, the bulk-copy latency dominates), longer rows want 1 stage and twice the
+  // resident CTAs (the row phase dominates).
   const double mean = n_local > 0 ? (double)nnz / (double)n_local : 0.0;
-  cfg = mean <= 40.0 ? 0 : 1;
-  if (const char* e = getenv("SPB_SPMV_CFG")) {
-    const int v = atoi(e);
-    if (v >= 0 && v < kNumCfgs) cfg = v;
-  }
-  const int tile = kCfgs[cfg].tile;
-  span = (max_row <= tile / 2) ? (tile - max_row) : tile / 2;
+  const int mean_c = (int)std::max(1.0, std::ceil(mean));
+  const int bytes_per_nnz = (int)sizeof(T) + 4;
+  int ct = env_int("SPB_SPMV_CT", 0);
+  if (ct <= 0) ct = (int)((21504 / ((int64_t)mean_c * bytes_per_nnz)) / 32 * 32);
+  int stages = env_int("SPB_SPMV_STAGES", 0);
+  if (stages <= 0) stages = mean <= 12.0 ? 2 : 1;
+  build_plan(ct, stages);
+  partials.alloc(sizeof(T) * 2 * (size_t)(2 * (int64_t)c->sm_count * 32 + 2));
+  red.alloc(sizeof(scal2) * 2);
+  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->dist && n_halo > 0) classify_tiles(this);
+}
+
+// Fix (consumer threads, stages), derive the tile size, cut the rows into tiles.
+template <typename T>
+void CsrMat<T>::build_plan(int ct, int stages) {
+  Ctx* c = ctx;
+  const double mean = n_local > 0 ? (double)nnz / (double)n_local : 0.0;
+  const int mean_c = (int)std::max(1.0, std::ceil(mean));
+  plan_gb = env_int("SPB_SPMV_ASYNCX", 0) ? 1 : 0;  // 1: x gathers via cp.async into shared memory
+  plan_stages = std::max(1, std::min(kMaxStages, stages));
+  const int rpt = std::max(1, env_int("SPB_SPMV_RPT", 1));
+  const int64_t row_extra = std::min<int64_t>(max_row, 4096);
+  plan_ct = std::max(32, std::min(256, ct / 32 * 32));
+  auto stage_bytes = [&](int64_t tile) { return (tile + 4) * (int64_t)((plan_gb ? 2 : 1) * sizeof(T) + 4) + (2 * 256 + 16) * (int64_t)sizeof(int64_t); };
+  int64_t tile = std::max<int64_t>(256, (((int64_t)plan_ct * rpt * mean_c + row_extra) + 3) & ~3LL);
+  const int64_t hard_cap = 200 * 1024;  // one CTA must fit
+  while (plan_stages > 1 && plan_stages * stage_bytes(tile) > hard_cap) --plan_stages;
+  while (tile > 256 && plan_stages * stage_bytes(tile) > hard_cap) tile = (tile / 2 + 3) & ~3LL;
+  const int max_tile = env_int("SPB_SPMV_MAXTILE", 0);
+  if (max_tile > 0) tile = std::min<int64_t>(tile, std::max(256, (max_tile + 3) & ~3));
+  plan_tile = (int)tile;
+  plan_rcap = std::max(64, 2 * plan_ct * rpt + 8);
+  span = (max_row <= plan_tile / 2) ? (plan_tile - max_row) : plan_tile / 2;
   if (span < 1) span = 1;
   ntiles = nnz / span + 1;
   tile_row.alloc(sizeof(int) * (size_t)(ntiles + 1));
@@ -372,32 +551,74 @@ void CsrMat<T>::analyze() {
                                                             ntiles, bufptr<int>(tile_row));
     check_launch("tile_rows_kernel");
   }
-  const int bps = ip64 ? spmv_blocks_per_sm<T, int64_t>(cfg) : spmv_blocks_per_sm<T, int32_t>(cfg);
-  const int64_t max_grid = (int64_t)c->sm_count * bps;
-  partials.alloc(sizeof(T) * 2 * (size_t)(2 * max_grid + 2));
-  red.alloc(sizeof(scal2) * 2);
+  plan_bps = ip64 ? spmv_blocks_per_sm<T, int64_t>(this) : spmv_blocks_per_sm<T, int32_t>(this);
+  const int bps_cap = env_int("SPB_SPMV_BPS", 0);
+  if (bps_cap > 0) plan_bps = std::min(plan_bps, bps_cap);
+  plan_bps = std::min(plan_bps, 32);
   SPB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+// The mkl_sparse_set_mv_hint + mkl_sparse_optimize analogue (src/mkl_mat.rs:81-148): time a few
+// (consumer threads, stages) plans with real SpMV launches on this matrix and keep the fastest.
+// The plan fixes the tile boundaries and therefore the summation order of the fused dot-product
+// epilogues; after tuning the choice is stable for the lifetime of the matrix.
+template <typename T>
+void CsrMat<T>::autotune() {
+  Ctx* c = ctx;
+  if (n_local == 0 || nnz == 0) return;
+  static const int cand[][2] = {{64, 1}, {128, 1}, {256, 1}, {64, 2}, {128, 2}, {192, 2}, {256, 2}};
+  DevBuf xb, yb;
+  xb.alloc(sizeof(T) * (size_t)n_local);
+  yb.alloc(sizeof(T) * (size_t)n_local);
+  SPB_CUDA(cudaMemsetAsync(xb.p, 0, xb.bytes, c->stream));
+  cudaEvent_t e0, e1;
+  SPB_CUDA(cudaEventCreate(&e0));
+  SPB_CUDA(cudaEventCreate(&e1));
+  int best = -1;
+  float best_ms = 0.f;
+  const int keep_ct = plan_ct, keep_st = plan_stages;
+  const int ncand = (int)(sizeof(cand) / sizeof(cand[0]));
+  for (int i = 0; i <= ncand; ++i) {
+    const int ct = i < ncand ? cand[i][0] : keep_ct, st = i < ncand ? cand[i][1] : keep_st;
+    build_plan(ct, st);
+    if (c->dist && n_halo > 0) classify_tiles(this);
+    mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
+    SPB_CUDA(cudaEventRecord(e0, c->stream));
+    for (int rep = 0; rep < 3; ++rep) mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
+    SPB_CUDA(cudaEventRecord(e1, c->stream));
+    SPB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (best < 0 || ms < best_ms) {
+      best = i;
+      best_ms = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  build_plan(best < ncand ? cand[best][0] : keep_ct, best < ncand ? cand[best][1] : keep_st);
   if (c->dist && n_halo > 0) classify_tiles(this);
 }
 
 template <typename T>
 void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
   Ctx* c = ctx;
-  const int bps = ip64 ? spmv_blocks_per_sm<T, int64_t>(cfg) : spmv_blocks_per_sm<T, int32_t>(cfg);
-  const int64_t max_grid = (int64_t)c->sm_count * bps;
+  const int64_t max_grid = (int64_t)c->sm_count * plan_bps;
   auto run = [&](const int* list, int64_t nt, int64_t part_off) -> int64_t {
     if (nt <= 0) return 0;
     const int grid = (int)std::min<int64_t>(nt, max_grid);
     if (ip64) {
       SpmvArgs<T, int64_t> a{bufptr<int64_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, bufptr<T>(halo), (int)n_local, y, w,
-                             bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value};
-      launch_spmv<T, int64_t>(c, cfg, a, epi_mode, conj_in, grid);
+                             bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
+                             plan_tile, plan_rcap, plan_stages};
+      launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
       SpmvArgs<T, int32_t> a{bufptr<int32_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, bufptr<T>(halo), (int)n_local, y, w,
-                             bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value};
-      launch_spmv<T, int32_t>(c, cfg, a, epi_mode, conj_in, grid);
+                             bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
+                             plan_tile, plan_rcap, plan_stages};
+      launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
     }
     return grid;
   };

@@ -110,7 +110,16 @@ def _rand_vec(n, dtype, seed=12345):
     return v.astype(dtype)
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+PLANS = [
+    {},  # the analysis step's own choice
+    {"SPB_SPMV_CT": "128", "SPB_SPMV_STAGES": "2"},
+    {"SPB_SPMV_CT": "256", "SPB_SPMV_STAGES": "3"},
+    {"SPB_SPMV_CT": "64", "SPB_SPMV_STAGES": "4", "SPB_SPMV_RPT": "3"},
+    {"SPB_SPMV_CT": "32", "SPB_SPMV_STAGES": "1", "SPB_SPMV_MAXTILE": "512"},
+]
+
+
+@pytest.mark.parametrize("cfg", range(len(PLANS)))
 @pytest.mark.parametrize(
     "make",
     [
@@ -122,7 +131,7 @@ def _rand_vec(n, dtype, seed=12345):
     ids=["lap7_f64", "helmholtz_c128", "convdiff27", "dirichlet2d"],
 )
 def test_spmv_bit_exact(sp, orc, make, cfg):
-    os.environ["SPB_SPMV_CFG"] = str(cfg)
+    os.environ.update(PLANS[cfg])
     try:
         A = make(orc)
         G = to_gpu(sp, A)
@@ -136,7 +145,8 @@ def test_spmv_bit_exact(sp, orc, make, cfg):
         assert np.array_equal(y2, yo)
         assert abs(d - do) <= 1e-13 * max(abs(do), 1.0)
     finally:
-        os.environ.pop("SPB_SPMV_CFG", None)
+        for k in PLANS[cfg]:
+            os.environ.pop(k, None)
 
 
 def test_spmv_ragged_and_long_rows(sp, orc):
