@@ -53,9 +53,18 @@ def _deps_mtime() -> float:
     return t
 
 
+# Per-file ptxas options.  spmv.cu: at -O2/-O3 ptxas re-schedules the row loop of the SpMV kernel
+# to minimise live ranges and sinks every x gather down to its first use, which serialises the
+# 8 gathers of a batch (one L2 round trip each); -O1 keeps the PTX order (8 column loads, 8
+# gathers, then the multiply-add chain).  Verified in SASS and on the B200 (profiles/).
+PTXAS_FLAGS = {"spmv.cu": os.environ.get("SPB_SPMV_PTXAS", "-O1")}
+
+
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     cmd = [_nvcc(), *NVCC_FLAGS, *_host_cxx(), "-c", os.path.join(CSRC, src), "-o", obj]
+    if PTXAS_FLAGS.get(src):
+        cmd.insert(1, f"-Xptxas={PTXAS_FLAGS[src]}")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -32,7 +32,7 @@ struct CsrMat : spb_op {
   // --- analysis (the mkl_sparse_optimize analogue): nnz-balanced row tiles -----------------
   int plan_ct = 128;     // consumer threads per CTA (one row per thread and tile)
   int plan_stages = 2;   // shared-memory stages of the bulk-copy ring
-  int plan_gb = 0;       // 1: x gathered with cp.async into shared memory, 0: into registers
+  int plan_gb = 0;       // reserved
   int plan_tile = 2048;  // non-zeros staged per tile
   int plan_rcap = 264;   // indptr entries staged per tile
   int plan_bps = 1;      // resident CTAs per SM (occupancy)

@@ -16,8 +16,7 @@
 //   * the consumer warps run one thread per row accumulating  acc = acc + x[col] * val
 //     SEQUENTIALLY IN CSR ORDER -- the same left fold as src/mat.rs:100-105 -- so y is
 //     bit-identical to the reference; lanes of a warp walk the same stencil diagonal, so the x
-//     gathers coalesce; they are issued as asynchronous global->shared copies (cp.async,
-//     LDGSTS, through L1), so every gather of a row is in flight at once whatever its length;
+//     gathers (ld.global.nc through L1, L2 evict_last) coalesce, and are issued 8 per batch;
 //   * dot-product epilogues (<r0,v>, <t,t>, <t,r>, conj(x).y) are folded in, so the Krylov loops
 //     never re-read the SpMV output for a reduction.
 // Algorithmic bytes per launch: nnz*(sizeof(T)+4) + (n+1)*sizeof(indptr) + 2*n*sizeof(T).
@@ -75,12 +74,15 @@ struct SpmvArgs {
   int stages;
 };
 
-template <typename T, bool CONJ_IN>
-__device__ __forceinline__ T gather_x(const T* x, const T* xh, int n_local, int c, uint64_t pol) {
-  // one unconditional load through a selected pointer: a branch around the load would make
-  // ptxas wait for each gather before issuing the next one
-  const T* p = (c < n_local) ? (x + c) : (xh + (c - n_local));
-  T v = ld_x(p, pol);
+// x entry for local column id c.  Single GPU (HALO = false): every column is owned.  Partitioned
+// (HALO = true): ids >= n_local live in the halo buffer; xh_adj = xh - n_local, so both cases are
+// base + c with a selected base -- one unconditional load (a branch around the load would make
+// ptxas wait for each gather before issuing the next).
+template <typename T, bool CONJ_IN, bool HALO>
+__device__ __forceinline__ T gather_x(const T* x, const T* xh_adj, int n_local, int c, uint64_t pol) {
+  const T* base = x;
+  if (HALO) base = (c < n_local) ? x : xh_adj;
+  T v = ld_x(base + c, pol);
   if (CONJ_IN) v = conj_of(v);
   return v;
 }
@@ -135,13 +137,6 @@ __device__ __forceinline__ void consumer_bar_sync(int nthreads) {
   asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ void cp_async_elem(double* smem_dst, const double* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_elem(cplx* smem_dst, const cplx* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(src) : "memory");
-}
-
 struct TileMeta {
   int r0, r1;     // rows of the tile
   int total;      // staged non-zeros counted from the 4-aligned base; -1 => long-row tile
@@ -181,7 +176,7 @@ __device__ __forceinline__ void row_range(const SpmvArgs<T, IP>& a, const TileMe
 }
 
 // blockDim.x = CT consumer threads + one producer warp.
-template <typename T, typename IP, bool AX, int EPI, bool CONJ_IN>
+template <typename T, typename IP, bool HALO, int EPI, bool CONJ_IN>
 __global__ void __launch_bounds__(288)
 spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -189,7 +184,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   const int VAL_BYTES = align16i((a.tile + 4) * (int)sizeof(T));
   const int COL_BYTES = align16i((a.tile + 4) * 4);
   const int IP_BYTES = align16i((a.rcap + 8) * (int)sizeof(IP));
-  const int STAGE_BYTES = (AX ? 2 : 1) * VAL_BYTES + COL_BYTES + IP_BYTES;  // vals | cols | indptr slice | [gathered x]
+  const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES;  // vals | cols | indptr slice
   const int STAGES = a.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
   uint64_t* empty = full + kMaxStages;
@@ -274,54 +269,38 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
       const T* s_val = reinterpret_cast<const T*>(stage);
       const int* s_col = reinterpret_cast<const int*>(stage + VAL_BYTES);
       const IP* s_ip = reinterpret_cast<const IP*>(stage + VAL_BYTES + COL_BYTES);
-      T* s_x = reinterpret_cast<T*>(smem_raw + s * STAGE_BYTES + VAL_BYTES + COL_BYTES + IP_BYTES);
-      (void)s_x;
-      if (m.total >= 0 && AX) {
-        // phase A: every x entry this thread's rows need is fetched with an asynchronous
-        // global->shared copy (cp.async, LDGSTS): no register result, so all gathers of the
-        // row(s) are in flight at once whatever the row length.  Lanes of a warp walk the same
-        // stencil diagonal, so each LDGSTS is a coalesced 256-byte request through L1.
-        for (int r = m.r0 + tid; r < m.r1; r += CT) {
-          int p0, p1;
-          row_range(a, m, s_ip, r, p0, p1);
-          for (int k = p0; k < p1; ++k) {
-            const int c = s_col[k];
-            const T* src = (c < a.n_local) ? (a.x + c) : (a.xh + (c - a.n_local));
-            cp_async_elem(s_x + k, src);
-          }
-        }
-        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
-        // phase B: sequential fold in CSR order out of shared memory (src/mat.rs:100-105);
-        // each thread reads only what it gathered itself, so no CTA barrier is needed.
+      if (m.total >= 0) {
+        // one thread per row: x gathers go to registers (ld.global.nc through L1, L2 evict_last),
+        // 8 per batch, then the sequential fold in CSR order (src/mat.rs:100-105).  Full batches
+        // carry no predicates; only the last (partial) batch of a row is clamped / predicated.
+        const T* xb = a.x;
+        const T* xh_adj = HALO ? (a.xh - a.n_local) : a.x;
+        const int nl = a.n_local;
         for (int r = m.r0 + tid; r < m.r1; r += CT) {
           int p0, p1;
           row_range(a, m, s_ip, r, p0, p1);
           T acc = zero_of<T>();
-#pragma unroll 4
-          for (int k = p0; k < p1; ++k) {
-            T xv = s_x[k];
-            if (CONJ_IN) xv = conj_of(xv);
-            acc = add(acc, mul(xv, s_val[k]));
+          int k = p0;
+          for (; k + 8 <= p1; k += 8) {
+            int c[8];
+            T xv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) c[j] = s_col[k + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HALO>(xb, xh_adj, nl, c[j], pol_x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = add(acc, mul(xv[j], s_val[k + j]));
           }
-          a.y[r] = acc;
-          epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
-        }
-      } else if (m.total >= 0) {
-        // register gathers (ld.global.nc through L1), 8 per batch, sequential fold in CSR order
-        for (int r = m.r0 + tid; r < m.r1; r += CT) {
-          int p0, p1;
-          row_range(a, m, s_ip, r, p0, p1);
-          T acc = zero_of<T>();
-          for (int k = p0; k < p1; k += 8) {
+          if (k < p1) {
             int c[8];
             T xv[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) c[j] = s_col[min(k + j, p1 - 1)];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, c[j], pol_x);
+            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HALO>(xb, xh_adj, nl, c[j], pol_x);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              if (k + j < p1) acc = add(acc, mul(xv[j], s_val[k + j]));  // src/mat.rs:100-105
+              if (k + j < p1) acc = add(acc, mul(xv[j], s_val[k + j]));
           }
           a.y[r] = acc;
           epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
@@ -334,7 +313,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           if (p1 - p0 > (IP)(a.tile / 2)) continue;
           T acc = zero_of<T>();
           for (IP k = p0; k < p1; ++k)
-            acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k], pol_x), a.vals[k]));
+            acc = add(acc, mul(gather_x<T, CONJ_IN, HALO>(a.x, HALO ? (a.xh - a.n_local) : a.x, a.n_local, a.cols[k], pol_x), a.vals[k]));
           a.y[r] = acc;
           epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
         }
@@ -343,7 +322,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           if (p1 - p0 <= (IP)(a.tile / 2)) continue;
           T acc = zero_of<T>();
           for (IP k = p0 + tid; k < p1; k += CT)
-            acc = add(acc, mul(gather_x<T, CONJ_IN>(a.x, a.xh, a.n_local, a.cols[k], pol_x), a.vals[k]));
+            acc = add(acc, mul(gather_x<T, CONJ_IN, HALO>(a.x, HALO ? (a.xh - a.n_local) : a.x, a.n_local, a.cols[k], pol_x), a.vals[k]));
           acc = consumer_sum(acc, s_red, CT);
           if (tid == 0) {
             a.y[r] = acc;
@@ -419,28 +398,28 @@ __global__ void finalize_partials_kernel(const T* partials, int64_t nblocks, sca
 // ---------------------------------------------------------------- launch plumbing
 template <typename T, typename IP>
 static size_t spmv_smem_bytes(const CsrMat<T>* m) {
-  const size_t stage = (m->plan_gb ? 2 : 1) * (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + align16i((m->plan_tile + 4) * 4) +
+  const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + align16i((m->plan_tile + 4) * 4) +
                        align16i((m->plan_rcap + 8) * (int)sizeof(IP));
   return m->plan_stages * stage + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(T) + 32;
 }
 
-// Runs f(kernel_pointer) for the kernel instance selected by (async_x, epi, conj).
-template <typename T, typename IP, bool AX, typename F>
+// Runs f(kernel_pointer) for the kernel instance selected by (halo, epi, conj).
+template <typename T, typename IP, bool HALO, typename F>
 static void with_kernel_ax(int epi, bool conj_in, F&& f) {
   constexpr bool CZ = ScalarTraits<T>::is_complex;
   if (CZ && conj_in) {
-    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, AX, EPI_NONE, CZ>);
-    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, AX, EPI_DOT_WY, CZ>);
-    else f(spmv_tma_kernel<T, IP, AX, EPI_TT_TR, CZ>);
+    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, HALO, EPI_NONE, CZ>);
+    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, HALO, EPI_DOT_WY, CZ>);
+    else f(spmv_tma_kernel<T, IP, HALO, EPI_TT_TR, CZ>);
   } else {
-    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, AX, EPI_NONE, false>);
-    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, AX, EPI_DOT_WY, false>);
-    else f(spmv_tma_kernel<T, IP, AX, EPI_TT_TR, false>);
+    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, HALO, EPI_NONE, false>);
+    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, HALO, EPI_DOT_WY, false>);
+    else f(spmv_tma_kernel<T, IP, HALO, EPI_TT_TR, false>);
   }
 }
 template <typename T, typename IP, typename F>
-static void with_kernel(int async_x, int epi, bool conj_in, F&& f) {
-  if (async_x) with_kernel_ax<T, IP, true>(epi, conj_in, f);
+static void with_kernel(int halo, int epi, bool conj_in, F&& f) {
+  if (halo) with_kernel_ax<T, IP, true>(epi, conj_in, f);
   else with_kernel_ax<T, IP, false>(epi, conj_in, f);
 }
 
@@ -449,7 +428,7 @@ static void launch_spmv(CsrMat<T>* m, const SpmvArgs<T, IP>& args, int epi, bool
   Ctx* ctx = m->ctx;
   LaunchScope ls(ctx, FAM_SPMV);
   const size_t smem = spmv_smem_bytes<T, IP>(m);
-  with_kernel<T, IP>(m->plan_gb, epi, conj_in, [&](auto kernel) {
+  with_kernel<T, IP>(m->n_halo > 0 ? 1 : 0, epi, conj_in, [&](auto kernel) {
     SPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, m->plan_ct + 32, smem, ctx->stream>>>(args);
   });
@@ -460,7 +439,7 @@ template <typename T, typename IP>
 static int spmv_blocks_per_sm(CsrMat<T>* m) {
   int nb = 0;
   const size_t smem = spmv_smem_bytes<T, IP>(m);
-  with_kernel<T, IP>(m->plan_gb, EPI_TT_TR, false, [&](auto kernel) {
+  with_kernel<T, IP>(m->n_halo > 0 ? 1 : 0, EPI_TT_TR, false, [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, m->plan_ct + 32, smem);
   });
@@ -522,12 +501,12 @@ void CsrMat<T>::build_plan(int ct, int stages) {
   Ctx* c = ctx;
   const double mean = n_local > 0 ? (double)nnz / (double)n_local : 0.0;
   const int mean_c = (int)std::max(1.0, std::ceil(mean));
-  plan_gb = env_int("SPB_SPMV_ASYNCX", 0) ? 1 : 0;  // 1: x gathers via cp.async into shared memory
+  plan_gb = 0;
   plan_stages = std::max(1, std::min(kMaxStages, stages));
   const int rpt = std::max(1, env_int("SPB_SPMV_RPT", 1));
   const int64_t row_extra = std::min<int64_t>(max_row, 4096);
   plan_ct = std::max(32, std::min(256, ct / 32 * 32));
-  auto stage_bytes = [&](int64_t tile) { return (tile + 4) * (int64_t)((plan_gb ? 2 : 1) * sizeof(T) + 4) + (2 * 256 + 16) * (int64_t)sizeof(int64_t); };
+  auto stage_bytes = [&](int64_t tile) { return (tile + 4) * (int64_t)(sizeof(T) + 4) + (2 * 256 + 16) * (int64_t)sizeof(int64_t); };
   int64_t tile = std::max<int64_t>(256, (((int64_t)plan_ct * rpt * mean_c + row_extra) + 3) & ~3LL);
   const int64_t hard_cap = 200 * 1024;  // one CTA must fit
   while (plan_stages > 1 && plan_stages * stage_bytes(tile) > hard_cap) --plan_stages;
