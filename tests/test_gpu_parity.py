@@ -360,6 +360,12 @@ def _check_solve(run, tol, A, rhs, strict=False, xs=None):
     else:
         ahead = np.concatenate([floor[2:], np.full(2, floor[-1])])[:m]  # tolerate a 2-iteration earlier onset
         allowed = np.maximum(HIST_RTOL, 16.0 * ahead)
+        # once the reference algorithm itself loses two digits to a mere re-ordering of its sums
+        # (an exact-arithmetic cancellation, e.g. <r0,v> = 0 on the Dirichlet fixture at iteration 3),
+        # the history value is rounding noise in every implementation: ratios of noise are
+        # heavy-tailed, so no finite multiple of a 4-sample spread bounds them.  From there on only
+        # the iteration count, the final residual and the solution are checked.
+        allowed = np.where(ahead >= 1e-2, np.inf, allowed)
         assert np.all(dev <= allowed), (int(np.argmax(dev / allowed)), dev.max())
         lo, hi = it_range
         slack = max(1, int(np.ceil(0.02 * o.iters)))
