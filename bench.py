@@ -208,21 +208,16 @@ def run_gpu(args):
 
     import sprsolve_b200 as sp
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from sprsolve_b200 import dist as spd
+
+    world, rank, local_rank = spd.env_world()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    spd.init_process_group("nccl", device=dev)
     ctx = sp.Context(local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
-    if world > 1:
-        ids = [sp.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(world, rank, ids[0])
+    spd.attach_communicator(ctx)  # rank 0 creates the communicator id, broadcast, spb_comm_init
 
     def barrier():
         if world > 1:
@@ -303,22 +298,22 @@ def run_gpu(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = args.steps * iters / (ms_total / 1e3)
 
-    # ---- e2e: host buffers in pinned memory, H2D + solve + D2H inside the timed region
+    # ---- e2e: the reference-facing call on HOST slices -- BiCGStab.precond_solve(M, rhs, x, ..)
+    #      = spb_solver_solve: H2D of rhs and of the initial guess x0, the solve, D2H of x, all
+    #      inside the timed region; rhs / x live in pinned host memory; x is in/out like the
+    #      reference's `&mut [T]`, so every step first resets it to x0 = 0 on the host.
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     rhs_h = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
-    x0_h = torch.zeros(n_loc, dtype=torch.float64, pin_memory=True)
-    xo_h = torch.empty(n_loc, dtype=torch.float64, pin_memory=True)
+    x_h = torch.zeros(n_loc, dtype=torch.float64, pin_memory=True)
     rhs_h.copy_(rhs)
-    rhs_d2 = torch.empty_like(rhs)
+    rhs_np, x_np = rhs_h.numpy(), x_h.numpy()
 
     def step_e2e():
-        rhs_d2.copy_(rhs_h, non_blocking=True)
-        x.copy_(x0_h, non_blocking=True)
+        x_h.zero_()
         try:
-            S.solve_dev(rhs_d2.data_ptr(), x.data_ptr(), iters, 1e-30, precond=M)
+            S.precond_solve(M, rhs_np, x_np, iters, 1e-30)
         except sp.InsufficientIterNum:
             pass
-        xo_h.copy_(x, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
 
     step_e2e()
     barrier()
@@ -330,6 +325,8 @@ def run_gpu(args):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = args.steps * iters / (ms_e2e / 1e3)
+    e2e_check = float(np.abs(x_np - x.cpu().numpy()).max())  # same iterate as the device-resident step
+    e2e_check = max_over_ranks(e2e_check)
 
     # ---- roofline: every SpMV launch of one more step bracketed by CUDA events
     ctx.profile_reset()
@@ -348,9 +345,14 @@ def run_gpu(args):
     n_products = 2 * iters + 1
     avg_ms = max_over_ranks(ms_spmv / n_products)
     achieved = b_spmv / (avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_spmv512_ncu_full.json")
+    if world == 1 and g == 512 and os.path.exists(tp):
+        traffic = float(json.load(open(tp))["traffic_bytes_per_launch"])
+        traffic_src = "profiles/r01_spmv512_ncu_full.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, same workload)"
     roofline = {
         "bound": "hbm", "kernel": "spmv_tma_kernel<double> (CSR SpMV, 27-pt, this rank's rows)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s (per GPU)", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s (per GPU)", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "bytes_per_launch": b_spmv, "avg_launch_ms": avg_ms, "launches_timed": n_spmv, "products_timed": n_products,
         "step_share": {"spmv_ms": ms_spmv, "vector_ms": ms_vec, "scalar_ms": ms_sc, "spmv_launches": n_spmv, "vector_launches": n_vec, "scalar_launches": n_sc},
         "iteration_bytes_model": 2 * b_spmv + 21 * n_loc * 8,
@@ -397,7 +399,8 @@ def run_gpu(args):
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world) | {"iters_per_step": iters},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_loc * 8 * world, "d2h_bytes_per_step": n_loc * 8 * world,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps, "api": "BiCGStab.precond_solve on pinned host slices (spb_solver_solve)",
+                    "max_abs_diff_vs_device_resident_step": e2e_check},
             "gpu_launches": launches, "clocks": clocks, "full_solve": full, "spmv_c2": spmv_c2, "setup_seconds": setup_s,
         }
         emit(line)

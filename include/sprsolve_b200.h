@@ -81,6 +81,10 @@ int spb_profile_reset(spb_ctx* ctx);
 int spb_comm_unique_id(void* id128);
 int spb_comm_init(spb_ctx* ctx, int world, int rank, const void* id128);
 int spb_comm_info(spb_ctx* ctx, int* world, int* rank);
+/* The row block [row_begin,row_end) spb_csr_create_stencil gives rank `rank` of `world`: contiguous
+ * rows cut at plane boundaries (z-slabs).  Pure host arithmetic (usable without a GPU). */
+int spb_stencil_partition(int kind, int64_t nx, int64_t ny, int64_t nz, int world, int rank,
+                          int64_t* row_begin, int64_t* row_end);
 
 /* ---- matrices: replaces MklMat::new (src/mkl_mat.rs:32-74) and the CsMatI operator ---------- */
 /* Copies a host CSR matrix to the device and analyses it (tiling = the mkl_sparse_optimize

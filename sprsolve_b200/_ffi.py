@@ -50,6 +50,7 @@ SIGNATURES = {
     "spb_comm_unique_id": (C.c_int, [vp]),
     "spb_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
     "spb_comm_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "spb_stencil_partition": (C.c_int, [C.c_int, i64, i64, i64, C.c_int, C.c_int, pi64, pi64]),
     "spb_csr_create": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, vp, C.c_int, vp, vp, pp]),
     "spb_csr_create_stencil": (C.c_int, [vp, C.c_int, C.c_int, i64, i64, i64, pdbl, C.c_int, pp]),
     "spb_csr_mv_hint": (C.c_int, [vp, C.c_int]),

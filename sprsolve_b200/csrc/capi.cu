@@ -173,6 +173,16 @@ int spb_comm_unique_id(void* id128) {
   SPB_CATCH
 }
 
+int spb_stencil_partition(int kind, int64_t nx, int64_t ny, int64_t nz, int world, int rank,
+                          int64_t* row_begin, int64_t* row_end) {
+  SPB_TRY
+  SPB_REQUIRE(row_begin && row_end && world >= 1 && rank >= 0 && rank < world, "bad partition arguments");
+  SPB_REQUIRE(kind >= 0 && kind <= SPB_STENCIL_CONVDIFF27 && nx >= 1 && ny >= 1 && nz >= 1, "bad grid");
+  stencil_partition(kind, nx, ny, kind == SPB_STENCIL_DIRICHLET2D ? 1 : nz, world, rank, row_begin, row_end);
+  return SPB_OK;
+  SPB_CATCH
+}
+
 int spb_comm_init(spb_ctx* c, int world, int rank, const void* id128) {
   SPB_TRY
   SPB_REQUIRE(c && id128 && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
