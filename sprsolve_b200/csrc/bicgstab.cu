@@ -256,12 +256,10 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     check_launch("bicg scalar kernel");
   };
   auto reduce_vec = [&]() {  // per-block partials of a vector kernel -> red (all ranks)
-    finalize_partials<T>(c, parts, grid, redp);
-    allreduce_sum(c, (double*)redp, 4);
+    finalize_allreduce<T>(c, parts, grid, redp);
   };
   auto reduce_spmv = [&]() {
-    Am->finalize_epilogue();
-    allreduce_sum(c, (double*)bufptr<scal2>(Am->red), 4);
+    Am->finalize_epilogue(true);
   };
   auto k_init = [&](int restart) {
     LaunchScope ls(c, FAM_VEC);

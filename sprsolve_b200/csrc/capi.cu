@@ -84,6 +84,7 @@ int spb_finalize(spb_ctx* c) {
   if (c->dist) {
     if (c->dist->comm_halo && c->dist->comm_halo != c->dist->comm) nccl().CommDestroy(c->dist->comm_halo);
     if (c->dist->comm) nccl().CommDestroy(c->dist->comm);
+    window_destroy(c->dist->scal);
     delete c->dist;
   }
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -205,6 +206,13 @@ int spb_comm_init(spb_ctx* c, int world, int rank, const void* id128) {
     throw;
   }
   c->dist = d;
+  // Data-path transport: stores into peer-mapped windows over NVLink (default) or NCCL
+  // (SPB_COMM=nccl; also the automatic choice when some peer cannot be mapped through CUDA IPC).
+  const char* tr = getenv("SPB_COMM");
+  if (world > 1 && !(tr && strcmp(tr, "nccl") == 0)) {
+    d->scal = window_create(c, sizeof(ScalWin));
+    d->peer = d->scal != nullptr;
+  }
   return SPB_OK;
   SPB_CATCH
 }
@@ -377,8 +385,7 @@ static void op_mul_dev(spb_op* op, const T* in, T* out, bool with_dot, double* d
   }
   auto* m = static_cast<CsrMat<T>*>(op);
   m->mul(in, out, EPI_DOT_WY, in, false);  // conj(v_in) . v_out fused (mkl_sparse_?_dotmv analogue)
-  m->finalize_epilogue();
-  allreduce_sum(c, (double*)bufptr<scal2>(m->red), 4);
+  m->finalize_epilogue(true);
   scal2 h[2];
   SPB_CUDA(cudaMemcpyAsync(h, m->red.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -709,7 +716,9 @@ int spb_solver_solve_dev(spb_solver* s, spb_op* precond, const void* d_rhs, void
   *resid = 0.0;
   if (hist_len) *hist_len = 0;
   if (precond && precond->dtype != s->dtype) SPB_FAIL(SPB_INVALID_ARG, "preconditioner dtype mismatch");
-  return s->solve_dev(precond, d_rhs, d_x, max_iter, tol, iters, resid, hist, hist_cap, hist_len);
+  const int rc = s->solve_dev(precond, d_rhs, d_x, max_iter, tol, iters, resid, hist, hist_cap, hist_len);
+  peer_check(s->ctx);
+  return rc;
   SPB_CATCH
 }
 
@@ -743,6 +752,7 @@ int spb_solver_solve(spb_solver* s, spb_op* precond, const void* rhs, int64_t n_
     SPB_CUDA(cudaMemcpyAsync(s->stage_x.p, x, esz * n_rhs, cudaMemcpyHostToDevice, c->stream));
   }
   const int rc = s->solve_dev(precond, s->stage_rhs.p, s->stage_x.p, max_iter, tol, iters, resid, hist, hist_cap, hist_len);
+  peer_check(c);
   if (n_rhs) SPB_CUDA(cudaMemcpyAsync(x, s->stage_x.p, esz * n_rhs, cudaMemcpyDeviceToHost, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   return rc;

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace spb {
 
@@ -18,6 +19,17 @@ struct HaloPeer {
   int rank;
   int64_t send_off, send_cnt;  // into sendbuf / send_idx
   int64_t recv_off, recv_cnt;  // into halo
+};
+
+struct PeerWindow;  // dist.cuh
+
+// Where this rank's boundary entries land in the neighbours' halo windows (peer transport).
+struct PutArgs {
+  int npeers;
+  void* dst0[kMaxPeers];                 // peer's halo payload + my offset in it (parity 0), T*
+  long long dst_stride[kMaxPeers];       // peer's n_halo: parity 1 lives dst_stride elements further
+  unsigned long long* rflag[kMaxPeers];  // &peer_head->flags[my rank]
+  long long send_off[kMaxPeers + 1];     // into send_idx
 };
 
 template <typename T>
@@ -50,7 +62,12 @@ struct CsrMat : spb_op {
   std::vector<HaloPeer> peers;
   std::vector<int32_t> halo_cols_global;  // sorted global ids of the halo slots (host copy)
   DevBuf tiles_interior, tiles_boundary;  // int32 tile lists (boundary = touches a halo column)
+  DevBuf tiles_all;                       // interior tiles followed by boundary tiles (fused launch)
   int64_t n_tiles_interior = 0, n_tiles_boundary = 0;
+  // peer transport: the halo lives in a window the neighbours write into (2 x n_halo, parity)
+  PeerWindow* halo_win = nullptr;
+  PutArgs put;
+  ~CsrMat();
 
   // --- host-slice staging (trait methods on &[T]) --------------------------------------------
   DevBuf stage_in, stage_out;
@@ -63,8 +80,9 @@ struct CsrMat : spb_op {
   // finalize_epilogue() (local sum only; the caller all-reduces when distributed).
   void mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in);
   int64_t last_partial_blocks = 0;
-  // Sums the per-block partials of the last mul() into red[0], red[1] (device).  Local sums.
-  void finalize_epilogue();
+  // Sums the per-block partials of the last mul() into red[0], red[1] (device).  allreduce: also
+  // sum over ranks (fused into the same kernel on the peer transport, ncclAllReduce otherwise).
+  void finalize_epilogue(bool allreduce = false);
 };
 
 template <typename T>
@@ -84,5 +102,9 @@ template <typename T>
 void halo_exchange_begin(CsrMat<T>* m, const T* x);  // pack + send/recv on the comm stream
 template <typename T>
 void halo_exchange_wait(CsrMat<T>* m);               // compute stream waits for the halo
+template <typename T>
+void halo_put(CsrMat<T>* m, const T* x);             // peer transport: store into the neighbours' windows
+template <typename T>
+void halo_release(CsrMat<T>* m);                     // frees the halo window (collective-free)
 
 }  // namespace spb

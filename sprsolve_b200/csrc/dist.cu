@@ -6,6 +6,8 @@
 #include <cub/cub.cuh>
 #include <dlfcn.h>
 
+#include <string.h>
+
 #include <algorithm>
 #include <mutex>
 
@@ -53,9 +55,101 @@ const NcclApi& nccl() {
 int Ctx::world() const { return dist ? dist->world : 1; }
 int Ctx::rank() const { return dist ? dist->rank : 0; }
 
+__global__ void peer_allreduce_kernel(double* v, int count, PeerPtrs pp) {
+  __shared__ double loc[4];
+  if (threadIdx.x < 4) loc[threadIdx.x] = (int)threadIdx.x < count ? v[threadIdx.x] : 0.0;
+  peer_allreduce4(loc, pp);
+  if ((int)threadIdx.x < count) v[threadIdx.x] = loc[threadIdx.x];
+}
+
 void allreduce_sum(Ctx* ctx, double* dev, size_t count) {
   if (!ctx->dist || ctx->dist->world == 1) return;
+  if (ctx->dist->peer) {
+    if (count > 4) SPB_FAIL(SPB_INVALID_ARG, "peer all-reduce carries at most 4 doubles");
+    LaunchScope ls(ctx, FAM_SCALAR);
+    peer_allreduce_kernel<<<1, 32, 0, ctx->stream>>>(dev, (int)count, ctx->dist->scal->ptrs());
+    check_launch("peer_allreduce_kernel");
+    return;
+  }
   SPB_NCCL(nccl().AllReduce(dev, dev, count, ncclFloat64, ncclSum, ctx->dist->comm, ctx->stream));
+}
+
+// ---------------------------------------------------------------- peer windows (CUDA IPC)
+PeerWindow* window_create(Ctx* ctx, size_t bytes) {
+  Dist* d = ctx->dist;
+  const int W = d->world, me = d->rank;
+  if (W > kMaxPeers) return nullptr;
+  auto* w = new PeerWindow();
+  w->world = W;
+  w->rank = me;
+  w->bytes = (bytes + 255) & ~(size_t)255;
+  w->mapped.assign(W, nullptr);
+  bool ok = true;
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  if (cudaMalloc(&w->local, w->bytes) != cudaSuccess) {
+    cudaGetLastError();
+    w->local = nullptr;
+    ok = false;
+  }
+  if (ok) {
+    SPB_CUDA(cudaMemsetAsync(w->local, 0, w->bytes, ctx->stream));
+    SPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cudaIpcGetMemHandle(&h, w->local) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+    }
+  }
+  // exchange the 64-byte handles (+ an ok word) through the set-up communicator; this is also the
+  // barrier that orders every rank's memset before any peer store
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  int64_t mine[9];
+  memcpy(mine, &h, 64);
+  mine[8] = ok ? 1 : 0;
+  std::vector<int64_t> all;
+  allgather_i64(ctx, mine, 9, all);
+  for (int q = 0; q < W; ++q) ok = ok && all[(size_t)q * 9 + 8] == 1;
+  if (ok) {
+    for (int q = 0; q < W; ++q) {
+      if (q == me) {
+        w->mapped[q] = w->local;
+        continue;
+      }
+      cudaIpcMemHandle_t hq;
+      memcpy(&hq, &all[(size_t)q * 9], 64);
+      if (cudaIpcOpenMemHandle(&w->mapped[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        w->mapped[q] = nullptr;
+        ok = false;
+      }
+    }
+  }
+  // agree on the outcome (a rank that failed to map one peer disables the transport for everyone)
+  int64_t okw = ok ? 1 : 0;
+  allgather_i64(ctx, &okw, 1, all);
+  for (int q = 0; q < W; ++q) ok = ok && all[q] == 1;
+  if (!ok) {
+    window_destroy(w);
+    return nullptr;
+  }
+  return w;
+}
+
+void window_destroy(PeerWindow* w) {
+  if (!w) return;
+  for (int q = 0; q < (int)w->mapped.size(); ++q)
+    if (q != w->rank && w->mapped[q]) cudaIpcCloseMemHandle(w->mapped[q]);
+  if (w->local) cudaFree(w->local);
+  delete w;
+}
+
+void peer_check(Ctx* ctx) {
+  if (!peer_mode(ctx)) return;
+  ScalWin* me = static_cast<ScalWin*>(ctx->dist->scal->local);
+  int err = 0;
+  SPB_CUDA(cudaMemcpyAsync(&err, &me->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SPB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err) SPB_FAIL(SPB_NCCL_ERROR, "timed out waiting for a peer rank (scalar all-reduce over peer memory)");
 }
 
 void allgather_i64(Ctx* ctx, const int64_t* host_in, size_t count, std::vector<int64_t>& out) {
@@ -138,6 +232,53 @@ __global__ void pack_kernel(const T* x, const int* idx, int64_t n, T* out) {
     out[i] = x[idx[i]];
 }
 
+// Peer transport: gather this rank's boundary entries of x and store them straight into the
+// neighbours' halo windows over NVLink; the CTA that finishes last publishes the sequence number
+// to every neighbour (release, system scope).
+template <typename T>
+__global__ void halo_put_kernel(const T* x, const int* idx, long long total, HaloHead* head, PutArgs pa) {
+  const unsigned long long seq = *((volatile unsigned long long*)&head->seq) + 1;
+  const long long par = (long long)(seq & 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int j = 0;
+    while (j + 1 < pa.npeers && i >= pa.send_off[j + 1]) ++j;
+    T* dst = static_cast<T*>(pa.dst0[j]) + par * pa.dst_stride[j] + (i - pa.send_off[j]);
+    *dst = x[idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&head->done, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      head->done = 0;
+      for (int j = 0; j < pa.npeers; ++j) st_release_sys(pa.rflag[j], seq);
+      *((volatile unsigned long long*)&head->seq) = seq;
+    }
+  }
+}
+
+template <typename T>
+void halo_put(CsrMat<T>* m, const T* x) {
+  Ctx* c = m->ctx;
+  const long long total = m->put.send_off[m->put.npeers];
+  LaunchScope ls(c, FAM_PACK);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), 148 * 4));
+  halo_put_kernel<T><<<grid, 256, 0, c->stream>>>(x, bufptr<int>(m->send_idx), total,
+                                                   static_cast<HaloHead*>(m->halo_win->local), m->put);
+  check_launch("halo_put_kernel");
+}
+
+template <typename T>
+void halo_release(CsrMat<T>* m) {
+  if (m->halo_win) {
+    cudaStreamSynchronize(m->ctx->stream);
+    window_destroy(m->halo_win);
+    m->halo_win = nullptr;
+  }
+}
+
 template <typename T>
 void csr_localize(CsrMat<T>* m) {
   Ctx* c = m->ctx;
@@ -204,7 +345,41 @@ void csr_localize(CsrMat<T>* m) {
     total_send += sc;
     m->peers.push_back(hp);
   }
-  m->halo.alloc(sizeof(T) * (size_t)std::max<int64_t>(nh, 1));
+  if (d->peer) {
+    // halo window: head + 2 x n_halo T (parity); every rank learns every n_halo to address parity 1
+    if ((int)m->peers.size() > kMaxPeers) SPB_FAIL(SPB_INVALID_ARG, "too many halo peers");
+    int64_t nh64 = nh;
+    std::vector<int64_t> nh_all;
+    allgather_i64(c, &nh64, 1, nh_all);
+    m->halo_win = window_create(c, kHaloHeadBytes + 2 * sizeof(T) * (size_t)std::max<int64_t>(nh, 1));
+    if (!m->halo_win) SPB_FAIL(SPB_NCCL_ERROR, "could not map the halo window of a peer (CUDA IPC); set SPB_COMM=nccl");
+    HaloHead hh;
+    memset(&hh, 0, sizeof(hh));
+    PutArgs& pa = m->put;
+    memset(&pa, 0, sizeof(pa));
+    pa.npeers = (int)m->peers.size();
+    hh.npeers = pa.npeers;
+    for (int j = 0; j < pa.npeers; ++j) {
+      const HaloPeer& hp = m->peers[j];
+      const int q = hp.rank;
+      hh.peer_rank[j] = q;
+      int64_t roff = 0;  // where my entries start in q's halo: q's slots are grouped by owner rank
+      for (int r = 0; r < me; ++r) roff += all_need[(size_t)q * W + r];
+      char* qbase = static_cast<char*>(m->halo_win->mapped[q]);
+      pa.dst0[j] = qbase + kHaloHeadBytes + sizeof(T) * (size_t)roff;
+      pa.dst_stride[j] = std::max<int64_t>(nh_all[q], 1);
+      pa.rflag[j] = &reinterpret_cast<HaloHead*>(qbase)->flags[me];
+      pa.send_off[j] = hp.send_off;
+    }
+    pa.send_off[pa.npeers] = total_send;
+    SPB_CUDA(cudaMemcpyAsync(m->halo_win->local, &hh, sizeof(hh), cudaMemcpyHostToDevice, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    int64_t token = 1;  // nobody starts putting before every head is initialised
+    std::vector<int64_t> sink;
+    allgather_i64(c, &token, 1, sink);
+  } else {
+    m->halo.alloc(sizeof(T) * (size_t)std::max<int64_t>(nh, 1));
+  }
   m->sendbuf.alloc(sizeof(T) * (size_t)std::max<int64_t>(total_send, 1));
   m->send_idx.alloc(sizeof(int) * (size_t)std::max<int64_t>(total_send, 1));
   // exchange the request lists (global ids), then make them local
@@ -244,6 +419,10 @@ void classify_tiles(CsrMat<T>* m) {
   m->tiles_boundary.alloc(sizeof(int) * std::max<size_t>(tb.size(), 1));
   if (!ti.empty()) SPB_CUDA(cudaMemcpyAsync(m->tiles_interior.p, ti.data(), sizeof(int) * ti.size(), cudaMemcpyHostToDevice, c->stream));
   if (!tb.empty()) SPB_CUDA(cudaMemcpyAsync(m->tiles_boundary.p, tb.data(), sizeof(int) * tb.size(), cudaMemcpyHostToDevice, c->stream));
+  std::vector<int> all(ti);
+  all.insert(all.end(), tb.begin(), tb.end());
+  m->tiles_all.alloc(sizeof(int) * std::max<size_t>(all.size(), 1));
+  if (!all.empty()) SPB_CUDA(cudaMemcpyAsync(m->tiles_all.p, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
@@ -286,5 +465,9 @@ template void halo_exchange_begin<double>(CsrMat<double>*, const double*);
 template void halo_exchange_begin<cplx>(CsrMat<cplx>*, const cplx*);
 template void halo_exchange_wait<double>(CsrMat<double>*);
 template void halo_exchange_wait<cplx>(CsrMat<cplx>*);
+template void halo_put<double>(CsrMat<double>*, const double*);
+template void halo_put<cplx>(CsrMat<cplx>*, const cplx*);
+template void halo_release<double>(CsrMat<double>*);
+template void halo_release<cplx>(CsrMat<cplx>*);
 
 }  // namespace spb

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace spb {
 
@@ -37,14 +38,42 @@ const NcclApi& nccl();  // throws SPB_NCCL_ERROR if libnccl.so.2 cannot be loade
     }                                                                                        \
   } while (0)
 
+// A block of device memory every rank of the node has mapped through CUDA IPC (NVLink peer
+// access): the transport of the scalar all-reduce and of the halo "put" (peer.cuh).
+struct PeerWindow {
+  void* local = nullptr;
+  size_t bytes = 0;
+  int world = 1, rank = 0;
+  std::vector<void*> mapped;  // [world], mapped[rank] == local
+  PeerPtrs ptrs() const {
+    PeerPtrs pp;
+    for (int q = 0; q < kMaxPeers; ++q) pp.p[q] = q < world ? mapped[q] : nullptr;
+    pp.world = world;
+    pp.rank = rank;
+    return pp;
+  }
+};
+// Collective over all ranks of ctx's communicator.  Returns nullptr (on every rank) when some
+// rank could not map some peer (no NVLink/IPC between them): the caller falls back to NCCL.
+PeerWindow* window_create(Ctx* ctx, size_t bytes);
+void window_destroy(PeerWindow* w);
+
 struct Dist {
   int world = 1, rank = 0;
-  ncclComm_t comm = nullptr;       // scalar all-reduces, on the compute stream
-  ncclComm_t comm_halo = nullptr;  // halo send/recv, on the comm stream
+  ncclComm_t comm = nullptr;       // scalar all-reduces (NCCL transport), set-up all-gathers
+  ncclComm_t comm_halo = nullptr;  // halo send/recv (NCCL transport), on the comm stream
   DevBuf scratch;                  // small device scratch for all-gathers
+  // peer-memory transport (default; SPB_COMM=nccl selects the NCCL transport instead)
+  bool peer = false;
+  PeerWindow* scal = nullptr;      // ScalWin of every rank
 };
 
-// In-place sum of `count` doubles across ranks on the compute stream (no-op when single GPU).
+inline bool peer_mode(const Ctx* ctx) { return ctx->dist && ctx->dist->peer; }
+// Raises SPB_NCCL_ERROR if a device-side spin on a peer flag timed out since the last check.
+void peer_check(Ctx* ctx);
+
+// In-place sum of `count` (<= 4) doubles across ranks on the compute stream (no-op when single
+// GPU).  Peer transport: one 32-thread kernel; NCCL transport: ncclAllReduce.
 void allreduce_sum(Ctx* ctx, double* dev, size_t count);
 void allgather_i64(Ctx* ctx, const int64_t* host_in, size_t count, std::vector<int64_t>& host_out);
 

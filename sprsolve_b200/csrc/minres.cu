@@ -271,8 +271,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
     check_launch("minres scalar kernel");
   };
   auto reduce_vec = [&]() {
-    finalize_partials<T>(c, parts, grid, redp);
-    allreduce_sum(c, (double*)redp, 4);
+    finalize_allreduce<T>(c, parts, grid, redp);
   };
   // b2 = <v_new, w_new> for a generic preconditioner (separate apply + conj_dot)
   auto generic_b2 = [&](T* vn, T* wn) {
@@ -340,8 +339,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
           const T* q = precond ? w : v;
           // v_new = A q with alpha = conj(q) . v_new   (CS: v_new = A conj(v), alpha = conj(v) . v_new)
           Am->mul(q, v_new, EPI_DOT_WY, q, cs);
-          Am->finalize_epilogue();
-          allreduce_sum(c, (double*)bufptr<scal2>(Am->red), 4);
+          Am->finalize_epilogue(true);
           scalar(mr_s_alpha<T>, st, bufptr<scal2>(Am->red));
           {
             LaunchScope ls(c, FAM_VEC);

@@ -23,6 +23,7 @@
 #include <cub/cub.cuh>
 
 #include "csr.cuh"
+#include "dist.cuh"
 #include "reduce.cuh"
 
 namespace spb {
@@ -72,6 +73,11 @@ struct SpmvArgs {
   int tile;      // staging capacity in non-zeros (multiple of 4)
   int rcap;      // staging capacity in indptr entries
   int stages;
+  // peer transport (fused interior + boundary launch): the halo payload is double buffered by the
+  // parity of hhead->seq, tiles [first_boundary, ntiles) of the list need the neighbours' puts
+  HaloHead* hhead;
+  long long halo_stride;
+  long long first_boundary;
 };
 
 // x entry for local column id c.  Single GPU (HALO = false): every column is owned.  Partitioned
@@ -206,6 +212,12 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
                                ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x
                                : 0;
   T e0 = zero_of<T>(), e1 = zero_of<T>();
+  const T* xh = a.xh;
+  unsigned long long hseq = 0;
+  if (HALO && a.hhead) {  // the put kernel queued before this launch has set seq for this exchange
+    hseq = a.hhead->seq;
+    xh += (long long)(hseq & 1) * a.halo_stride;
+  }
 
   if (tid >= CT) {
     // ------------------------------------------------------------ producer (one lane)
@@ -214,8 +226,17 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
       const uint64_t pol_stream = l2_policy_evict_first();
       int s = 0;
       uint32_t ph = 0;
+      bool halo_ready = !(HALO && a.hhead);
       for (int64_t i = 0; i < my_tiles; ++i) {
         const int64_t ti = blockIdx.x + i * gridDim.x;
+        if (HALO && !halo_ready && ti >= a.first_boundary) {
+          // boundary tiles gather x entries the neighbours store into this rank's halo window:
+          // wait for their flags (they were sent before the neighbours' own SpMV, i.e. about one
+          // interior pass ago).  Consumers only touch a tile after the full-barrier below.
+          for (int j = 0; j < a.hhead->npeers; ++j)
+            if (!spin_until_ge(&a.hhead->flags[a.hhead->peer_rank[j]], hseq)) a.hhead->error = 1;
+          halo_ready = true;
+        }
         const int tile = a.tile_list ? a.tile_list[ti] : (int)ti;
         const int r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1];
         const IP st = a.indptr[r0], en = a.indptr[r1];
@@ -274,7 +295,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
         // 8 per batch, then the sequential fold in CSR order (src/mat.rs:100-105).  Full batches
         // carry no predicates; only the last (partial) batch of a row is clamped / predicated.
         const T* xb = a.x;
-        const T* xh_adj = HALO ? (a.xh - a.n_local) : a.x;
+        const T* xh_adj = HALO ? (xh - a.n_local) : a.x;
         const int nl = a.n_local;
         for (int r = m.r0 + tid; r < m.r1; r += CT) {
           int p0, p1;
@@ -313,7 +334,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           if (p1 - p0 > (IP)(a.tile / 2)) continue;
           T acc = zero_of<T>();
           for (IP k = p0; k < p1; ++k)
-            acc = add(acc, mul(gather_x<T, CONJ_IN, HALO>(a.x, HALO ? (a.xh - a.n_local) : a.x, a.n_local, a.cols[k], pol_x), a.vals[k]));
+            acc = add(acc, mul(gather_x<T, CONJ_IN, HALO>(a.x, HALO ? (xh - a.n_local) : a.x, a.n_local, a.cols[k], pol_x), a.vals[k]));
           a.y[r] = acc;
           epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
         }
@@ -322,7 +343,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           if (p1 - p0 <= (IP)(a.tile / 2)) continue;
           T acc = zero_of<T>();
           for (IP k = p0 + tid; k < p1; k += CT)
-            acc = add(acc, mul(gather_x<T, CONJ_IN, HALO>(a.x, HALO ? (a.xh - a.n_local) : a.x, a.n_local, a.cols[k], pol_x), a.vals[k]));
+            acc = add(acc, mul(gather_x<T, CONJ_IN, HALO>(a.x, HALO ? (xh - a.n_local) : a.x, a.n_local, a.cols[k], pol_x), a.vals[k]));
           acc = consumer_sum(acc, s_red, CT);
           if (tid == 0) {
             a.y[r] = acc;
@@ -386,13 +407,23 @@ __global__ void max_row_kernel(const IP* indptr, int64_t n, unsigned long long* 
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);  // integer atomic: order-independent
 }
 
-template <typename T>
-__global__ void finalize_partials_kernel(const T* partials, int64_t nblocks, scal2* red) {
+// Fixed-order sum of the per-CTA epilogue partials; PEER: the sum over ranks is done in the same
+// CTA through the peers' scalar windows (peer.cuh) -- no separate collective launch.
+template <typename T, bool PEER>
+__global__ void finalize_partials_kernel(const T* partials, int64_t nblocks, scal2* red, PeerPtrs pp) {
   __shared__ T scratch[32];
+  __shared__ double loc[4];
   for (int slot = 0; slot < 2; ++slot) {
     const T s = block_sum_partials(partials + slot, nblocks, 2, scratch);
-    if (threadIdx.x == 0) red[slot] = to_scal2(s);
+    if (threadIdx.x == 0) {
+      const scal2 v = to_scal2(s);
+      loc[2 * slot] = v.re;
+      loc[2 * slot + 1] = v.im;
+    }
   }
+  if (PEER) peer_allreduce4(loc, pp);
+  else __syncthreads();
+  if (threadIdx.x < 2) red[threadIdx.x] = scal2{loc[2 * threadIdx.x], loc[2 * threadIdx.x + 1]};
 }
 
 // ---------------------------------------------------------------- launch plumbing
@@ -492,7 +523,7 @@ void CsrMat<T>::analyze() {
   partials.alloc(sizeof(T) * 2 * (size_t)(2 * (int64_t)c->sm_count * 32 + 2));
   red.alloc(sizeof(scal2) * 2);
   SPB_CUDA(cudaStreamSynchronize(c->stream));
-  if (c->dist && n_halo > 0) classify_tiles(this);
+  if (c->dist && !peers.empty()) classify_tiles(this);
 }
 
 // Fix (consumer threads, stages), derive the tile size, cut the rows into tiles.
@@ -560,7 +591,7 @@ void CsrMat<T>::autotune() {
   for (int i = 0; i <= ncand; ++i) {
     const int ct = i < ncand ? cand[i][0] : keep_ct, st = i < ncand ? cand[i][1] : keep_st;
     build_plan(ct, st);
-    if (c->dist && n_halo > 0) classify_tiles(this);
+    if (c->dist && !peers.empty()) classify_tiles(this);
     mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
     SPB_CUDA(cudaEventRecord(e0, c->stream));
     for (int rep = 0; rep < 3; ++rep) mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
@@ -576,33 +607,48 @@ void CsrMat<T>::autotune() {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   build_plan(best < ncand ? cand[best][0] : keep_ct, best < ncand ? cand[best][1] : keep_st);
-  if (c->dist && n_halo > 0) classify_tiles(this);
+  if (c->dist && !peers.empty()) classify_tiles(this);
 }
 
 template <typename T>
 void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
   Ctx* c = ctx;
   const int64_t max_grid = (int64_t)c->sm_count * plan_bps;
+  HaloHead* hhead = nullptr;
+  long long hstride = 0, first_boundary = 0;
+  const T* halo_ptr = bufptr<T>(halo);
+  if (halo_win) {
+    hhead = static_cast<HaloHead*>(halo_win->local);
+    hstride = std::max<int64_t>(n_halo, 1);
+    first_boundary = n_tiles_interior;
+    halo_ptr = reinterpret_cast<const T*>(static_cast<char*>(halo_win->local) + kHaloHeadBytes);
+  }
   auto run = [&](const int* list, int64_t nt, int64_t part_off) -> int64_t {
     if (nt <= 0) return 0;
     const int grid = (int)std::min<int64_t>(nt, max_grid);
     if (ip64) {
       SpmvArgs<T, int64_t> a{bufptr<int64_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
-                             list, nt, x, bufptr<T>(halo), (int)n_local, y, w,
+                             list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
-                             plan_tile, plan_rcap, plan_stages};
+                             plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary};
       launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
       SpmvArgs<T, int32_t> a{bufptr<int32_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
-                             list, nt, x, bufptr<T>(halo), (int)n_local, y, w,
+                             list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
-                             plan_tile, plan_rcap, plan_stages};
+                             plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary};
       launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
     }
     return grid;
   };
-  if (n_halo == 0 || !c->dist) {
+  if (!c->dist || peers.empty()) {
     last_partial_blocks = run(nullptr, ntiles, 0);
+  } else if (halo_win) {
+    // peer transport: put the boundary entries into the neighbours' windows, then ONE launch --
+    // interior tiles first, the kernel itself waits for the neighbours' flags before its first
+    // boundary tile (the NVLink transfer hides behind the interior pass)
+    halo_put(this, x);
+    last_partial_blocks = run(bufptr<int>(tiles_all), n_tiles_interior + n_tiles_boundary, 0);
   } else {
     // interior rows overlap the NVLink halo exchange; boundary rows wait for it
     halo_exchange_begin(this, x);
@@ -614,11 +660,23 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
 }
 
 template <typename T>
-void CsrMat<T>::finalize_epilogue() {
-  LaunchScope ls(ctx, FAM_SCALAR);
-  finalize_partials_kernel<T><<<1, 256, 0, ctx->stream>>>(bufptr<T>(partials), last_partial_blocks,
-                                                          bufptr<scal2>(red));
-  check_launch("finalize_partials_kernel");
+void CsrMat<T>::finalize_epilogue(bool allreduce) {
+  {
+    LaunchScope ls(ctx, FAM_SCALAR);
+    if (allreduce && peer_mode(ctx))
+      finalize_partials_kernel<T, true><<<1, 256, 0, ctx->stream>>>(bufptr<T>(partials), last_partial_blocks,
+                                                                    bufptr<scal2>(red), ctx->dist->scal->ptrs());
+    else
+      finalize_partials_kernel<T, false><<<1, 256, 0, ctx->stream>>>(bufptr<T>(partials), last_partial_blocks,
+                                                                     bufptr<scal2>(red), PeerPtrs{});
+    check_launch("finalize_partials_kernel");
+  }
+  if (allreduce && !peer_mode(ctx)) allreduce_sum(ctx, (double*)bufptr<scal2>(red), 4);
+}
+
+template <typename T>
+CsrMat<T>::~CsrMat() {
+  halo_release(this);
 }
 
 template struct CsrMat<double>;

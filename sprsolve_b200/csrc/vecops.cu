@@ -4,22 +4,45 @@
 // coalesced grid-stride loops over a grid that is a multiple of the SM count.
 #include "vecops.cuh"
 
+#include "dist.cuh"
+
 namespace spb {
 
-template <typename T>
-__global__ void finalize_partials_k(const T* partials, int64_t nblocks, scal2* red) {
+// PEER: the sum over ranks happens in the same CTA through the peers' scalar windows (peer.cuh).
+template <typename T, bool PEER>
+__global__ void finalize_partials_k(const T* partials, int64_t nblocks, scal2* red, PeerPtrs pp) {
   __shared__ T scratch[32];
+  __shared__ double loc[4];
   for (int slot = 0; slot < 2; ++slot) {
     const T s = block_sum_partials(partials + slot, nblocks, 2, scratch);
-    if (threadIdx.x == 0) red[slot] = to_scal2(s);
+    if (threadIdx.x == 0) {
+      const scal2 v = to_scal2(s);
+      loc[2 * slot] = v.re;
+      loc[2 * slot + 1] = v.im;
+    }
   }
+  if (PEER) peer_allreduce4(loc, pp);
+  else __syncthreads();
+  if (threadIdx.x < 2) red[threadIdx.x] = scal2{loc[2 * threadIdx.x], loc[2 * threadIdx.x + 1]};
 }
 
 template <typename T>
 void finalize_partials(Ctx* c, const T* partials, int64_t nblocks, scal2* red) {
   LaunchScope ls(c, FAM_SCALAR);
-  finalize_partials_k<T><<<1, 256, 0, c->stream>>>(partials, nblocks, red);
+  finalize_partials_k<T, false><<<1, 256, 0, c->stream>>>(partials, nblocks, red, PeerPtrs{});
   check_launch("finalize_partials");
+}
+
+template <typename T>
+void finalize_allreduce(Ctx* c, const T* partials, int64_t nblocks, scal2* red) {
+  if (!peer_mode(c)) {
+    finalize_partials<T>(c, partials, nblocks, red);
+    allreduce_sum(c, (double*)red, 4);
+    return;
+  }
+  LaunchScope ls(c, FAM_SCALAR);
+  finalize_partials_k<T, true><<<1, 256, 0, c->stream>>>(partials, nblocks, red, c->dist->scal->ptrs());
+  check_launch("finalize_allreduce");
 }
 
 template <typename T, int KIND>
@@ -111,6 +134,7 @@ void vec_zero(Ctx* c, int64_t n, T* x) {
 
 #define SPB_INST(T)                                                                          \
   template void finalize_partials<T>(Ctx*, const T*, int64_t, scal2*);                       \
+  template void finalize_allreduce<T>(Ctx*, const T*, int64_t, scal2*);                      \
   template void vec_reduce<T>(Ctx*, int, int64_t, const T*, const T*, T*, scal2*);           \
   template void vec_axpy<T>(Ctx*, int64_t, T, const T*, T*);                                 \
   template void vec_axpby<T>(Ctx*, int64_t, T, const T*, T, T*);                             \

@@ -35,6 +35,9 @@ __device__ __forceinline__ void write_partials(T e0, T e1, T* partials) {
 // Fixed-order sum of the block partials into red[0], red[1] (one tiny CTA).
 template <typename T>
 void finalize_partials(Ctx* c, const T* partials, int64_t nblocks, scal2* red);
+// Same, followed by the sum over ranks (fused into the same kernel on the peer transport).
+template <typename T>
+void finalize_allreduce(Ctx* c, const T* partials, int64_t nblocks, scal2* red);
 
 // vecalg on device pointers ---------------------------------------------------------------
 // kind: 0 = dot (no conjugate, vecalg.rs:557-561), 1 = conj_dot (:564-568), 2 = sum |x|^2 (:601-605)
