@@ -136,6 +136,11 @@ int spb_diag_precond_from_csr(spb_op* mat, spb_op** out);
  * SPB_ZERO_DIAGONAL like src/gauss_seidel.rs:72-78.  Single-GPU only. */
 int spb_gs_precond_create(spb_op* mat, int mode, spb_op** out);
 int spb_gs_levels(spb_op* gs, int64_t* n_levels_fwd, int64_t* n_levels_bwd);
+/* Block-wavefront schedule of the sweep (diagnostics): info = {fwd ok, rows per block, blocks, fwd chunks,
+ * fwd local levels (max over blocks), ring stages, shared memory bytes, bwd ok, bwd chunks, bwd local levels,
+ * poll-timeout flag, rhs slots, other-side slots, packed bytes, 0, 0}.  stats (optional, SPB_GS_STATS=1 at
+ * create): per block of the last sweep {clocks, clocks waiting for the ring, poll retries, chunks}. */
+int spb_gs_schedule_info(spb_op* gs, int64_t info[16], int64_t* stats, int64_t stats_cap);
 
 /* ---- vecalg (src/vecalg.rs:19-144) on host slices; out / a / b are (re,im) pairs -------------- */
 int spb_vec_dot(spb_ctx* ctx, int dtype, int64_t n, const void* x, const void* y, double out[2]);

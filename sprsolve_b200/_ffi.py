@@ -68,6 +68,7 @@ SIGNATURES = {
     "spb_diag_precond_from_csr": (C.c_int, [vp, pp]),
     "spb_gs_precond_create": (C.c_int, [vp, C.c_int, pp]),
     "spb_gs_levels": (C.c_int, [vp, pi64, pi64]),
+    "spb_gs_schedule_info": (C.c_int, [vp, pi64, pi64, i64]),
     "spb_vec_dot": (C.c_int, [vp, C.c_int, i64, vp, vp, pdbl]),
     "spb_vec_conj_dot": (C.c_int, [vp, C.c_int, i64, vp, vp, pdbl]),
     "spb_vec_norm2": (C.c_int, [vp, C.c_int, i64, vp, pdbl]),

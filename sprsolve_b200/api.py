@@ -369,6 +369,18 @@ class GaussSeidelPrecond(MatVecMul):
         _check(F.lib().spb_gs_levels(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def schedule_info(self, stats_blocks: int = 0):
+        """Diagnostics of the block-wavefront sweep schedule (spb_gs_schedule_info)."""
+        info = (C.c_int64 * 16)()
+        st = (C.c_int64 * max(4 * stats_blocks, 1))()
+        _check(F.lib().spb_gs_schedule_info(self._h, info, st if stats_blocks else None, 4 * stats_blocks))
+        keys = ["fwd_ok", "block_rows", "blocks", "fwd_chunks", "fwd_local_levels", "stages", "smem_bytes", "bwd_ok",
+                "bwd_chunks", "bwd_local_levels", "poll_timeout", "rhs_slots", "other_slots", "packed_bytes"]
+        d = {k: int(info[i]) for i, k in enumerate(keys)}
+        if stats_blocks:
+            d["stats"] = np.array(st[: 4 * stats_blocks], dtype=np.int64).reshape(-1, 4)
+        return d
+
 
 # --------------------------------------------------------------------------- solvers
 class _Solver:

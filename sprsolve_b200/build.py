@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libsprsolve_b200.so")
 
 SOURCES = [
     "spmv.cu", "create.cu", "dist.cu", "vecops.cu", "ops.cu", "solver_common.cu",
-    "bicgstab.cu", "minres.cu", "gs_solver.cu", "capi.cu",
+    "bicgstab.cu", "minres.cu", "gs_solver.cu", "gs_wave.cu", "capi.cu",
 ]
 
 NVCC_FLAGS = [

@@ -531,6 +531,37 @@ int spb_gs_levels(spb_op* gs, int64_t* nf, int64_t* nb) {
   SPB_CATCH
 }
 
+namespace {
+template <typename T>
+void gs_schedule_info_impl(spb_op* gs, int64_t* info, int64_t* stats, int64_t cap) {
+  auto* g = static_cast<GsOp<T>*>(gs);
+  Ctx* c = g->ctx;
+  int flags[4] = {0, 0, 0, 0}, flagsb[4] = {0, 0, 0, 0};
+  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  if (g->wfwd.ok) SPB_CUDA(cudaMemcpy(flags, g->wfwd.ticket.p, sizeof(flags), cudaMemcpyDeviceToHost));
+  if (g->wbwd.ok) SPB_CUDA(cudaMemcpy(flagsb, g->wbwd.ticket.p, sizeof(flagsb), cudaMemcpyDeviceToHost));
+  const int64_t v[16] = {g->wfwd.ok, g->wfwd.block_rows, g->wfwd.nblocks, g->wfwd.nchunks, g->wfwd.local_levels_max,
+                         g->wfwd.stages, (int64_t)g->wfwd.smem_bytes, g->wbwd.ok, g->wbwd.nchunks, g->wbwd.local_levels_max,
+                         flags[1] | flagsb[1], g->wfwd.rhs_slots, g->wfwd.xg_slots, (int64_t)g->wfwd.stat.bytes, 0, 0};
+  if (info) for (int i = 0; i < 16; ++i) info[i] = v[i];
+  if (stats && g->wave_stats.p) {
+    const int64_t m = std::min<int64_t>(cap, 4 * (int64_t)g->wfwd.nblocks);
+    SPB_CUDA(cudaMemcpy(stats, g->wave_stats.p, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+  }
+}
+}  // namespace
+
+int spb_gs_schedule_info(spb_op* gs, int64_t info[16], int64_t* stats, int64_t stats_cap) {
+  SPB_TRY
+  SPB_REQUIRE(gs && gs->kind == OP_GS, "not a Gauss-Seidel operator");
+  if (gs->dtype == SPB_F64)
+    gs_schedule_info_impl<double>(gs, info, stats, stats_cap);
+  else
+    gs_schedule_info_impl<cplx>(gs, info, stats, stats_cap);
+  return SPB_OK;
+  SPB_CATCH
+}
+
 // ---------------------------------------------------------------- vecalg on host slices
 namespace {
 template <typename T>

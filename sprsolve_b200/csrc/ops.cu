@@ -6,6 +6,7 @@
 // order, so each x_i is bit-identical to the sequential loop.  One persistent cooperative kernel
 // walks all levels with a grid-wide barrier in between (no kernel launch per level).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ops.cuh"
@@ -271,6 +272,17 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
     op->bad_row = bad == ~0ULL ? -1 : (int64_t)bad;
     build_levels(c, n, ip, cols, true, op->fwd);
     build_levels(c, n, ip, cols, false, op->bwd);
+    {  // block-wavefront schedules (gs_wave.cu) -- the fast path
+      std::vector<T> vals((size_t)A->nnz);
+      if (A->nnz) SPB_CUDA(cudaMemcpyAsync(vals.data(), A->vals.p, sizeof(T) * A->nnz, cudaMemcpyDeviceToHost, c->stream));
+      SPB_CUDA(cudaStreamSynchronize(c->stream));
+      wave_build<T>(A, ip, cols, vals, false, op->wfwd);
+      if (mode == SPB_GS_SYMMETRIC) wave_build<T>(A, ip, cols, vals, true, op->wbwd);
+      if (getenv("SPB_GS_STATS") && op->wfwd.ok) {
+        op->wave_stats.alloc(sizeof(long long) * 4 * (size_t)op->wfwd.nblocks);
+        SPB_CUDA(cudaMemset(op->wave_stats.p, 0, op->wave_stats.bytes));
+      }
+    }
   } catch (...) {
     delete op;
     throw;
@@ -305,6 +317,14 @@ static void launch_sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T
 
 template <typename T>
 static void sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, const T* hi, T* out) {
+  // fast path: block-wavefront sweep.  It pre-fills `out`, so out must be the produced side only.
+  const bool fwd = &ls == &M->fwd;
+  WaveSched& ws = fwd ? M->wfwd : M->wbwd;
+  const T* other = fwd ? hi : lo;
+  if (ws.ok && (fwd ? lo : hi) == out && out != rhs && out != other) {
+    wave_sweep<T>(M, ws, rhs, other, out);
+    return;
+  }
   if (M->A->ip64)
     launch_sweep<T, int64_t>(M, ls, rhs, lo, hi, out);
   else

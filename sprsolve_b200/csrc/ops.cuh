@@ -19,14 +19,53 @@ struct LevelSched {
   std::vector<int> level_ptr_host;
 };
 
+// Block-wavefront schedule of one sweep direction (gs_wave.cu).  The rows are cut into blocks of
+// `block_rows` consecutive rows, one CTA each; inside a block the rows are ordered by LOCAL level
+// (dependencies on rows of the same block only) and packed, together with everything static a row
+// needs, into a byte stream of chunks that the CTA's producer lane pulls through shared memory
+// with bulk async copies.  Dependencies on rows of other blocks are resolved by polling the
+// output vector (sentinel pre-fill), dependencies inside the block through shared memory.
+struct WaveChunk {
+  long long soff;     // byte offset of the chunk's static part in `stat`
+  long long rhs_off;  // element offset of the chunk's slice of the permuted rhs
+  long long xg_off;   // element offset of the chunk's slice of the gathered other-side x
+  int sbytes;         // static bytes (multiple of 16)
+  int nrows;
+  int xg_cnt;
+  int pad;
+};
+
+struct WaveSched {
+  bool ok = false;
+  bool backward = false;
+  int block_rows = 0;
+  int nblocks = 0;
+  int64_t nchunks = 0;
+  int64_t rhs_slots = 0, xg_slots = 0;
+  int stage_static = 0, stage_rows = 0, stage_other = 0;  // per-stage capacities
+  int stages = 0;
+  size_t smem_bytes = 0;
+  int64_t local_levels_max = 0;
+  DevBuf stat;       // packed static chunks
+  DevBuf chunks;     // WaveChunk [nchunks]
+  DevBuf blk_chunk;  // int32 [nblocks+1], blocks in PROCESSING order
+  DevBuf rowmap;     // int32 [rhs_slots]: row id of the slot, -1 = padding
+  DevBuf ocol;       // int32 [xg_slots]: column of the other-side entry, -1 = padding
+  DevBuf rhsp;       // T [rhs_slots]  (per apply)
+  DevBuf xg;         // T [xg_slots]   (per apply)
+  DevBuf ticket;     // int32 [4]: block ticket, timeout flag
+};
+
 template <typename T>
 struct GsOp : spb_op {
   CsrMat<T>* A = nullptr;
   int mode = SPB_GS_FORWARD;
   DevBuf diag;          // T [n] cached diagonal (src/gauss_seidel.rs:81)
-  LevelSched fwd, bwd;  // lower / upper pattern
+  LevelSched fwd, bwd;  // lower / upper pattern (global levels: reported, and the fallback sweep)
+  WaveSched wfwd, wbwd; // block-wavefront schedules (the fast path)
   DevBuf tmp;           // T [n]: forward result for the symmetric variant
   DevBuf barrier;       // grid barrier words
+  DevBuf wave_stats;    // int64 [4 * nblocks] per-block clocks of the last wavefront sweep (SPB_GS_STATS=1)
   int64_t bad_row = -1; // first row with a missing / tiny diagonal (src/gauss_seidel.rs:72-78)
 };
 
@@ -48,6 +87,15 @@ void gs_apply(GsOp<T>* M, const T* in, T* out);
 // Rows < i are read from x_new (already updated), rows > i from x_old.
 template <typename T>
 void gs_solver_sweep(GsOp<T>* M, const T* rhs, const T* x_old, T* x_new);
+
+// gs_wave.cu: block-wavefront sweep.  wave_build analyses one direction (host CSR copy in);
+// wave_sweep runs out = sweep(rhs) where the produced side reads `out` itself and the other
+// triangle reads `other` (null: skipped, i.e. a sweep from zero).  out must not alias rhs/other.
+template <typename T>
+void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<int>& cols,
+                const std::vector<T>& vals, bool backward, WaveSched& ws);
+template <typename T>
+void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out);
 
 // Generic operator application used by the solvers: CSR -> SpMV, Diag, GS.
 template <typename T>

@@ -288,6 +288,61 @@ def test_gauss_seidel_sweep_bit_exact(sp, orc, symmetric):
     assert e.value.row == 0
 
 
+def _random_sorted_csr(orc, n, density, seed, dtype=np.float64):
+    """Random pattern (sorted columns, full diagonal, diagonally dominant) -- not a stencil, so rows
+    depend on rows far away and on many blocks of the wavefront schedule."""
+    rng = np.random.default_rng(seed)
+    ip, idx, val = [0], [], []
+    for i in range(n):
+        k = rng.integers(0, max(2, int(density * n)))
+        cols = np.unique(np.concatenate([rng.integers(0, n, size=k), [i]]))
+        v = rng.uniform(-1, 1, size=cols.size).astype(dtype)
+        if np.issubdtype(dtype, np.complexfloating):
+            v = v + 1j * rng.uniform(-1, 1, size=cols.size)
+        v[cols == i] = cols.size + 1.0
+        idx.append(cols)
+        val.append(v)
+        ip.append(ip[-1] + cols.size)
+    return orc.Csr(n, np.array(ip, np.int64), np.concatenate(idx).astype(np.int32), np.concatenate(val))
+
+
+@pytest.mark.parametrize("knobs", [
+    {},                                                                       # default blocking
+    {"SPB_GS_BLOCK_ROWS": "7"},                                               # almost every dependency crosses blocks (polls)
+    {"SPB_GS_BLOCK_ROWS": "96", "SPB_GS_STAGE_ROWS": "8", "SPB_GS_STAGE_BYTES": "1024", "SPB_GS_STAGE_OTHER": "64"},  # levels split over chunks
+    {"SPB_GS_BLOCK_ROWS": "33", "SPB_GS_STAGES": "2"},
+    {"SPB_GS_LEGACY": "1"},                                                   # fallback: global levels + grid barrier
+])
+def test_gauss_seidel_wavefront_schedules(sp, orc, knobs, monkeypatch):
+    """The block-wavefront sweep (csrc/gs_wave.cu) under every blocking / staging regime is bit-identical
+    to the sequential sweep of src/gauss_seidel.rs:111-125 -- forward, symmetric, and the stationary
+    solver's sweep that reads the old iterate on the other triangle."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    mats = [orc.gen_lap3d7(12, 11, 10, shift=0.05), orc.gen_convdiff27(9, 8, 7), _random_sorted_csr(orc, 700, 0.02, 5),
+            orc.gen_lap3d7(7, 6, 5, shift=0.5 + 0.5j, dtype=np.complex128), _random_sorted_csr(orc, 300, 0.03, 6, np.complex128)]
+    for A in mats:
+        G = to_gpu(sp, A)
+        for symmetric in (False, True):
+            P = sp.GaussSeidelPrecond(G, symmetric=symmetric)
+            info = P.schedule_info()
+            assert info["fwd_ok"] == (0 if "SPB_GS_LEGACY" in knobs else 1)
+            for rep in range(2):  # the second apply re-uses the schedule (ticket / sentinel reset)
+                v = _rand_vec(A.n, A.dtype)
+                out = np.zeros(A.n, A.dtype)
+                P.mul_vec(v, out)
+                assert np.array_equal(out, orc.gs_apply(A, v, symmetric))
+            assert P.schedule_info()["poll_timeout"] == 0
+        if not np.issubdtype(A.dtype, np.complexfloating):
+            rhs = orc.spmv(A, np.ones(A.n))
+            x = np.zeros(A.n)
+            o = orc.gauss_seidel(A, rhs, max_iter=25, eps=0.0)  # not converged after 25 sweeps: Err, x holds sweep 25
+            assert o.status == orc.INSUFFICIENT_ITER
+            with pytest.raises(sp.InsufficientIterNum):
+                sp.GaussSeidel(G).solve(rhs, x, 25, 0.0)
+            assert np.array_equal(x, o.x)
+
+
 # ------------------------------------------------------------------ solvers vs oracle
 def _oracle(orc, solver, A, rhs, pc, tol, max_iter, x0=None):
     kw = dict(max_iter=max_iter, tol=tol, x0=x0, hist_cap=max_iter + 1)
