@@ -542,7 +542,7 @@ void gs_schedule_info_impl(spb_op* gs, int64_t* info, int64_t* stats, int64_t ca
   if (g->wbwd.ok) SPB_CUDA(cudaMemcpy(flagsb, g->wbwd.ticket.p, sizeof(flagsb), cudaMemcpyDeviceToHost));
   const int64_t v[16] = {g->wfwd.ok, g->wfwd.block_rows, g->wfwd.nblocks, g->wfwd.nchunks, g->wfwd.local_levels_max,
                          g->wfwd.stages, (int64_t)g->wfwd.smem_bytes, g->wbwd.ok, g->wbwd.nchunks, g->wbwd.local_levels_max,
-                         flags[1] | flagsb[1], g->wfwd.rhs_slots, g->wfwd.xg_slots, (int64_t)g->wfwd.stat.bytes, 0, 0};
+                         flags[1] | flagsb[1], g->wfwd.rhs_slots, g->wfwd.aux_slots, (int64_t)g->wfwd.stat.bytes, 0, 0};
   if (info) for (int i = 0; i < 16; ++i) info[i] = v[i];
   if (stats && g->wave_stats.p) {
     const int64_t m = std::min<int64_t>(cap, 4 * (int64_t)g->wfwd.nblocks);

@@ -28,10 +28,10 @@ struct LevelSched {
 struct WaveChunk {
   long long soff;     // byte offset of the chunk's static part in `stat`
   long long rhs_off;  // element offset of the chunk's slice of the permuted rhs
-  long long xg_off;   // element offset of the chunk's slice of the gathered other-side x
+  long long aux_off;  // element offset of the chunk's slice of the per-apply other-triangle data
   int sbytes;         // static bytes (multiple of 16)
   int nrows;
-  int xg_cnt;
+  int aux_cnt;        // backward: nrows (pre-folded lower part); forward: Wo * nrows products
   int pad;
 };
 
@@ -41,7 +41,7 @@ struct WaveSched {
   int block_rows = 0;
   int nblocks = 0;
   int64_t nchunks = 0;
-  int64_t rhs_slots = 0, xg_slots = 0;
+  int64_t rhs_slots = 0, aux_slots = 0;
   int stage_static = 0, stage_rows = 0, stage_other = 0;  // per-stage capacities
   int stages = 0;
   size_t smem_bytes = 0;
@@ -50,9 +50,10 @@ struct WaveSched {
   DevBuf chunks;     // WaveChunk [nchunks]
   DevBuf blk_chunk;  // int32 [nblocks+1], blocks in PROCESSING order
   DevBuf rowmap;     // int32 [rhs_slots]: row id of the slot, -1 = padding
-  DevBuf ocol;       // int32 [xg_slots]: column of the other-side entry, -1 = padding
+  DevBuf aux_base;   // int64 [rhs_slots] (forward only): first aux element of the row's products
+  DevBuf aux_dims;   // int32 [2 * rhs_slots] (forward only): stride (rows of the chunk), Wo
   DevBuf rhsp;       // T [rhs_slots]  (per apply)
-  DevBuf xg;         // T [xg_slots]   (per apply)
+  DevBuf aux;        // T [aux_slots]  (per apply)
   DevBuf ticket;     // int32 [4]: block ticket, timeout flag
 };
 

@@ -43,6 +43,9 @@ if os.environ.get("SPB_GS_STATS"):
     st = info.pop("stats")
     print("stats (last sweep = backward): clocks med/max", int(np.median(st[:, 0])), int(st[:, 0].max()), "ring-wait med/max", int(np.median(st[:, 1])), int(st[:, 1].max()),
           "poll retries total", int(st[:, 2].sum()), "t0 barrier clocks med/max", int(np.median(st[:, 3])), int(st[:, 3].max()))
+    for b in (0, 1, 2, 3, 8, 16, 32, 64, 96, 127, 147):
+        if b < len(st):
+            print("  ticket", b, "clocks", int(st[b, 0]), "ring", int(st[b, 1]), "spins", int(st[b, 2]), "bar", int(st[b, 3]))
 print(info)
 knobs = {k: v for k, v in os.environ.items() if k.startswith("SPB_GS")}
 print(f"{kind} {g}^3 levels={lv} sgs_apply_ms={ms:.4f} us_per_level={1e3 * ms / (lv[0] + lv[1]):.3f} checksum={float(z.sum()):.17g} {knobs}")
