@@ -97,6 +97,23 @@ int spb_csr_create(spb_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_
 /* Generates the matrix on the device (this rank's row block when a communicator is set). */
 int spb_csr_create_stencil(spb_ctx* ctx, int kind, int dtype, int64_t nx, int64_t ny, int64_t nz,
                            const double* params, int nparams, spb_op** out);
+
+/* ---- other layouts on the callers' side of the operator (single GPU; all arrays are host) ------
+ * CSC: the reference's CsMatViewI operator also accepts CSC storage and multiplies column by column,
+ * v_out[row] += v_in[col] * value (src/mat.rs:130-142; KAT src/mat.rs:208-229).  The matrix is
+ * transposed on the device with a stable sort, which keeps every output element's accumulation
+ * order, so mul_vec is bit-identical to that loop.  indptr has ncols+1 entries. */
+int spb_csc_create(spb_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, const void* indptr,
+                   int indptr_bits, const int32_t* row_indices, const void* values, spb_op** out);
+/* Triplets: sprs::TriMat::to_csr as used by the reference's fixtures (tests/test_minres.rs:65-119,
+ * tests/test_complex_solve.rs:99-213): sorted by (row, column), duplicates summed in input order. */
+int spb_csr_create_from_triplets(spb_ctx* ctx, int dtype, int64_t nrows, int64_t ncols, int64_t nnz,
+                                 const int32_t* rows, const int32_t* cols, const void* values,
+                                 spb_op** out);
+/* Matrix Market coordinate file (real / integer / pattern / complex; general / symmetric /
+ * skew-symmetric / hermitian), the format the reference's fixtures were exported from
+ * (tests/test_complex_solve.rs:14).  Non-square or array-format files: SPB_INCOMPATIBLE_FORMAT. */
+int spb_csr_read_matrix_market(spb_ctx* ctx, int dtype, const char* path, spb_op** out);
 /* MklMat::mv_hint / mv_and_dotmv_hint (src/mkl_mat.rs:81-148), i.e. mkl_sparse_set_mv_hint +
  * mkl_sparse_optimize: time a handful of launch plans with real SpMV launches on this matrix and
  * keep the fastest.  Optional: spb_csr_create already picks a static plan.  The plan fixes the

@@ -147,10 +147,12 @@ def spmv(A: Csr, x: np.ndarray, parallel: bool = False) -> np.ndarray:
 def spmv_csc(nrows, ncols, indptr, indices, data, x) -> np.ndarray:
     indptr = np.ascontiguousarray(indptr, dtype=np.int64)
     indices = np.ascontiguousarray(indices, dtype=np.int32)
-    data = np.ascontiguousarray(data, dtype=np.float64)
-    x = np.ascontiguousarray(x, dtype=np.float64)
-    y = np.empty(nrows, dtype=np.float64)
-    lib().orc_spmv_csc_d(_i64(nrows), _i64(ncols), _ptr(indptr), _ptr(indices), _ptr(data), _ptr(x), _ptr(y))
+    dt = np.complex128 if (np.iscomplexobj(data) or np.iscomplexobj(x)) else np.float64
+    data = np.ascontiguousarray(data, dtype=dt)
+    x = np.ascontiguousarray(x, dtype=dt)
+    y = np.empty(nrows, dtype=dt)
+    fn = lib().orc_spmv_csc_z if dt is np.complex128 else lib().orc_spmv_csc_d
+    fn(_i64(nrows), _i64(ncols), _ptr(indptr), _ptr(indices), _ptr(data), _ptr(x), _ptr(y))
     return y
 
 

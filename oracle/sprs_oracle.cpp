@@ -746,6 +746,17 @@ void orc_spmv_csc_d(int64_t nrows, int64_t ncols, const int64_t* ip, const int32
     for (int64_t k = ip[c]; k < ip[c + 1]; ++k) y[idx[k]] += m * a[k];
   }
 }
+void orc_spmv_csc_z(int64_t nrows, int64_t ncols, const int64_t* ip, const int32_t* idx,
+                    const double* a_, const double* x_, double* y_) {
+  const cplx* a = (const cplx*)a_;
+  const cplx* x = (const cplx*)x_;
+  cplx* y = (cplx*)y_;
+  for (int64_t i = 0; i < nrows; ++i) y[i] = cplx{0.0, 0.0};
+  for (int64_t c = 0; c < ncols; ++c) {
+    const cplx m = x[c];
+    for (int64_t k = ip[c]; k < ip[c + 1]; ++k) y[idx[k]] = add(y[idx[k]], mul(m, a[k]));  // *t += *multiplier * value
+  }
+}
 void orc_spmv_dot_d(int64_t n, const int64_t* ip, const int32_t* idx, const double* a,
                     const double* x, double* y, double* out) {
   Csr<double> A{n, ip, idx, a};

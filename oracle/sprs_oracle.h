@@ -56,6 +56,8 @@ void orc_spmv_par_z(int64_t n, const int64_t* indptr, const int32_t* idx, const 
                     const double* x, double* y);
 void orc_spmv_csc_d(int64_t nrows, int64_t ncols, const int64_t* indptr, const int32_t* idx,
                     const double* a, const double* x, double* y);
+void orc_spmv_csc_z(int64_t nrows, int64_t ncols, const int64_t* indptr, const int32_t* idx,
+                    const double* a, const double* x, double* y);
 void orc_spmv_dot_d(int64_t n, const int64_t* indptr, const int32_t* idx, const double* a,
                     const double* x, double* y, double* out);
 void orc_spmv_dot_z(int64_t n, const int64_t* indptr, const int32_t* idx, const double* a,

@@ -20,6 +20,7 @@ C ABI; nothing here does arithmetic.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -284,6 +285,53 @@ class GpuCsrMat(MatVecMul):
         )
         _check(st)
         return cls(h, ctx, data.dtype.type)
+
+    @staticmethod
+    def _values(data):
+        data = np.ascontiguousarray(data)
+        if data.dtype not in (np.float64, np.complex128):
+            data = data.astype(np.complex128 if np.iscomplexobj(data) else np.float64)
+        return data
+
+    @classmethod
+    def from_csc(cls, indptr, row_indices, data, shape=None, ctx: Context | None = None):
+        """A CSC matrix as the operator (the CSC branch of CsMatViewI::mul_vec, src/mat.rs:130-142):
+        transposed on the device with a stable sort, so every output element keeps the accumulation
+        order of the reference's column-by-column loop."""
+        ctx = ctx or default_context()
+        data = cls._values(data)
+        row_indices = np.ascontiguousarray(row_indices, dtype=np.int32)
+        indptr = np.ascontiguousarray(indptr)
+        bits = 32 if indptr.dtype == np.int32 else 64
+        if bits == 64:
+            indptr = indptr.astype(np.int64)
+        n = indptr.size - 1
+        shape = shape or (n, n)
+        h = C.c_void_p()
+        _check(F.lib().spb_csc_create(ctx._h, _dtype_code(data.dtype), shape[0], shape[1], _ptr(indptr), bits, _ptr(row_indices), _ptr(data), C.byref(h)))
+        return cls(h, ctx, data.dtype.type)
+
+    @classmethod
+    def from_triplets(cls, n: int, rows, cols, data, ctx: Context | None = None):
+        """sprs::TriMat::to_csr (tests/test_minres.rs:65-119): sorted by (row, column), duplicates
+        summed in input order; assembled on the device."""
+        ctx = ctx or default_context()
+        data = cls._values(data)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        if not (rows.size == cols.size == data.size):
+            raise ValueError("rows, cols and data must have the same length")
+        h = C.c_void_p()
+        _check(F.lib().spb_csr_create_from_triplets(ctx._h, _dtype_code(data.dtype), n, n, rows.size, _ptr(rows), _ptr(cols), _ptr(data), C.byref(h)))
+        return cls(h, ctx, data.dtype.type)
+
+    @classmethod
+    def read_matrix_market(cls, path: str, dtype=np.float64, ctx: Context | None = None):
+        """Matrix Market coordinate file -> device CSR (spb_csr_read_matrix_market)."""
+        ctx = ctx or default_context()
+        h = C.c_void_p()
+        _check(F.lib().spb_csr_read_matrix_market(ctx._h, _dtype_code(dtype), os.fsencode(path), C.byref(h)))
+        return cls(h, ctx, np.dtype(dtype).type)
 
     @classmethod
     def from_stencil(cls, kind: int, nx: int, ny: int | None = None, nz: int | None = None, params=(), dtype=np.float64, ctx=None):

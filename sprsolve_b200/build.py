@@ -21,7 +21,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libsprsolve_b200.so")
 
 SOURCES = [
-    "spmv.cu", "create.cu", "dist.cu", "vecops.cu", "ops.cu", "solver_common.cu",
+    "spmv.cu", "create.cu", "ingest.cu", "dist.cu", "vecops.cu", "ops.cu", "solver_common.cu",
     "bicgstab.cu", "minres.cu", "gs_solver.cu", "gs_wave.cu", "capi.cu",
 ]
 

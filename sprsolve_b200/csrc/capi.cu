@@ -265,6 +265,61 @@ int spb_csr_create_stencil(spb_ctx* c, int kind, int dtype, int64_t nx, int64_t 
   SPB_CATCH
 }
 
+int spb_csc_create(spb_ctx* c, int dtype, int64_t nrows, int64_t ncols, const void* indptr, int indptr_bits,
+                   const int32_t* row_indices, const void* values, spb_op** out) {
+  SPB_TRY
+  SPB_REQUIRE(c && out && indptr, "null argument");
+  *out = nullptr;
+  use_device(c);
+  if (nrows != ncols) {
+    set_last_error("Not a square matrix");
+    return SPB_INCOMPATIBLE_FORMAT;
+  }
+  if (dtype == SPB_F64)
+    *out = csr_from_csc<double>(c, nrows, indptr, indptr_bits, row_indices, values);
+  else if (dtype == SPB_C128)
+    *out = csr_from_csc<cplx>(c, nrows, indptr, indptr_bits, row_indices, values);
+  else
+    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  return SPB_OK;
+  SPB_CATCH
+}
+
+int spb_csr_create_from_triplets(spb_ctx* c, int dtype, int64_t nrows, int64_t ncols, int64_t nnz, const int32_t* rows,
+                                 const int32_t* cols, const void* values, spb_op** out) {
+  SPB_TRY
+  SPB_REQUIRE(c && out && (nnz == 0 || (rows && cols && values)), "null argument");
+  *out = nullptr;
+  use_device(c);
+  if (nrows != ncols) {
+    set_last_error("Not a square matrix");
+    return SPB_INCOMPATIBLE_FORMAT;
+  }
+  if (dtype == SPB_F64)
+    *out = csr_from_triplets<double>(c, nrows, nnz, rows, cols, values);
+  else if (dtype == SPB_C128)
+    *out = csr_from_triplets<cplx>(c, nrows, nnz, rows, cols, values);
+  else
+    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  return SPB_OK;
+  SPB_CATCH
+}
+
+int spb_csr_read_matrix_market(spb_ctx* c, int dtype, const char* path, spb_op** out) {
+  SPB_TRY
+  SPB_REQUIRE(c && out && path, "null argument");
+  *out = nullptr;
+  use_device(c);
+  if (dtype == SPB_F64)
+    *out = csr_from_matrix_market<double>(c, path);
+  else if (dtype == SPB_C128)
+    *out = csr_from_matrix_market<cplx>(c, path);
+  else
+    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  return SPB_OK;
+  SPB_CATCH
+}
+
 static int rehint(spb_op* m) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR, "not a CSR matrix");

@@ -176,6 +176,31 @@ CsrMat<T>* csr_from_host(Ctx* ctx, int64_t n_global, int64_t row_begin, int64_t 
   return m;
 }
 
+// ---------------------------------------------------------------- from device arrays (ingest.cu)
+template <typename T>
+CsrMat<T>* csr_adopt_device(Ctx* ctx, int64_t n, int64_t nnz, DevBuf&& indptr32, DevBuf&& cols, DevBuf&& vals) {
+  auto* m = new CsrMat<T>();
+  try {
+    m->ctx = ctx;
+    m->kind = OP_CSR;
+    m->dtype = ScalarTraits<T>::dtype;
+    m->n_global = m->n_local = n;
+    m->row_begin = 0;
+    m->nnz = nnz;
+    m->ip64 = false;
+    m->indptr = std::move(indptr32);
+    m->cols = std::move(cols);  // both already carry the kPad tail
+    m->vals = std::move(vals);
+    finish_create(m);
+  } catch (...) {
+    delete m;
+    throw;
+  }
+  return m;
+}
+template CsrMat<double>* csr_adopt_device<double>(Ctx*, int64_t, int64_t, DevBuf&&, DevBuf&&, DevBuf&&);
+template CsrMat<cplx>* csr_adopt_device<cplx>(Ctx*, int64_t, int64_t, DevBuf&&, DevBuf&&, DevBuf&&);
+
 // ---------------------------------------------------------------- on-device generators
 void stencil_partition(int kind, int64_t nx, int64_t ny, int64_t nz, int world, int rank,
                        int64_t* row_begin, int64_t* row_end) {

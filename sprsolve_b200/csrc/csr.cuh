@@ -93,6 +93,14 @@ template <typename T>
 CsrMat<T>* csr_from_stencil(Ctx* ctx, int kind, int64_t nx, int64_t ny, int64_t nz,
                             const double* params, int nparams);
 
+// ingest.cu: the other layouts callers start from (single GPU).  All arrays are host pointers.
+template <typename T>
+CsrMat<T>* csr_from_triplets(Ctx* ctx, int64_t n, int64_t nnz, const int32_t* rows, const int32_t* cols, const void* vals);
+template <typename T>
+CsrMat<T>* csr_from_csc(Ctx* ctx, int64_t n, const void* indptr, int indptr_bits, const int32_t* row_indices, const void* vals);
+template <typename T>
+CsrMat<T>* csr_from_matrix_market(Ctx* ctx, const char* path);
+
 // dist.cu: turn GLOBAL column ids into local + halo ids, build the exchange plan.
 template <typename T>
 void csr_localize(CsrMat<T>* m);

@@ -17,7 +17,7 @@ HIST_K = 60  # residual-history entries kept per solver case
 
 # name -> (kind, solver, preconditioner, tol, max_iter)
 CASES = {
-    "c1_dirichlet2d_48_jacobi_bicgstab": ("solve", "bicgstab", "diag", 1e-8, 5000),
+    "c1_dirichlet2d_96_jacobi_bicgstab": ("solve", "bicgstab", "diag", 1e-8, 5000),
     "c5_convdiff27_12x11x10_jacobi_bicgstab": ("solve", "bicgstab", "diag", 1e-8, 500),
     "c3_lap3d7_12_shift005_sgs_minres": ("solve", "minres", "gs_sym", 1e-8, 400),
     "c3_lap3d7_12_shift005_minres": ("solve", "minres", None, 1e-8, 400),
@@ -42,7 +42,7 @@ def _vec(n, dtype, phase=0.0):
 def build_inputs(orc, name):
     """Returns (A, rhs_or_x)."""
     if name.startswith("c1_") :
-        return orc.gen_dirichlet2d(48)
+        return orc.gen_dirichlet2d(96)
     if name.startswith("c5_"):
         A = orc.gen_convdiff27(12, 11, 10)
         return A, orc.spmv(A, np.ones(A.n))
@@ -51,7 +51,7 @@ def build_inputs(orc, name):
         return A, orc.spmv(A, np.ones(A.n))
     if name.startswith("c4_"):
         A = orc.gen_lap3d7(10, 10, 10, shift=0.5 + 0.5j, dtype=np.complex128)
-        return A, orc.spmv(A, np.full(A.n, 1 + 1j))
+        return A, orc.spmv(A, _vec(A.n, np.complex128))  # a structureless solution: (1+i)*ones makes the history rounding noise
     if name.startswith("gs_solver_"):
         return orc.gen_dirichlet2d(10)
     if name in ("op_spmv_convdiff27_9x8x7", "op_jacobi_convdiff27_9x8x7"):
@@ -83,7 +83,26 @@ def oracle_outputs(orc, name):
         kw = dict(max_iter=max_iter, tol=tol, hist_cap=max_iter + 1)
         o = orc.csminres(A, v, **kw) if solver == "csminres" else getattr(orc, solver)(A, v, pc=pc_of(A, pc), **kw)
         assert o.status == orc.OK, (name, o.status)
-        return {"iters": np.int64(o.iters), "resid": np.float64(o.resid), "hist": o.hist[:HIST_K].copy(), "x": o.x}
+        # How far the REFERENCE ALGORITHM ITSELF moves when only the order of its long sums changes
+        # (serial fold vs OpenMP partial sums over 2/3/5/8 threads = the MKL / rayon build flavours):
+        # the bound any implementation that re-orders reductions can be held to.
+        k = min(HIST_K, len(o.hist))
+        floor = np.zeros(k)
+        its = [o.iters]
+        try:
+            for nt in (2, 3, 5, 8):
+                orc.set_threads(nt)
+                orc.set_mode(2)
+                w = orc.csminres(A, v, **kw) if solver == "csminres" else getattr(orc, solver)(A, v, pc=pc_of(A, pc), **kw)
+                its.append(w.iters)
+                m = min(k, len(w.hist))
+                floor[:m] = np.maximum(floor[:m], np.abs(w.hist[:m] - o.hist[:m]) / np.abs(o.hist[:m]))
+                floor[m:] = np.inf
+        finally:
+            orc.set_mode(0)
+            orc.set_threads(orc.max_threads())
+        return {"iters": np.int64(o.iters), "resid": np.float64(o.resid), "hist": o.hist[:HIST_K].copy(), "x": o.x,
+                "reorder_floor": np.maximum.accumulate(floor), "iters_range": np.array([min(its), max(its)], np.int64)}
     if kind == "gs_solver":
         o = orc.gauss_seidel(A, v, max_iter=max_iter, eps=tol)
         return {"iters": np.int64(o.iters), "resid": np.float64(o.resid), "hist": o.hist[:HIST_K].copy(), "x": o.x,
