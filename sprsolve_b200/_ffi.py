@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsprsolve_b200.so")
+LIB_PATH = os.environ.get("SPB_LIB") or os.path.join(_HERE, "lib", "libsprsolve_b200.so")  # SPB_LIB: A/B builds (tools/)
 
 # spb_status (include/sprsolve_b200.h)
 OK = 0

@@ -11,10 +11,15 @@
 //     ordered by a named barrier between levels;
 //   * every block walks its rows in GLOBAL level order (longest dependency chain over the whole
 //     triangle), so all blocks advance along the same wavefront whatever the block boundaries;
-//   * a dependency on another block is read from the output vector in global memory.  The vector
-//     is pre-filled with a sentinel (a NaN payload no arithmetic produces) and every x_i is
-//     published with ONE 8/16-byte store, so the value itself says that it is ready.  The polling
-//     is done by two HELPER warps per CTA that run ahead of the row threads and drop each value
+//   * a dependency on another block travels through a MAILBOX in global memory: at analysis time
+//     every chunk of a consumer block gets a contiguous range of mailbox slots, one per distinct
+//     outside column, in the order it needs them, and the producing row gets the list of slots
+//     that want its value.  The mailbox is pre-filled with a sentinel (a NaN payload no arithmetic
+//     produces) and a value is delivered with ONE 8/16-byte store per slot, so the value itself
+//     says that it is ready -- no flags, no fences.  The polling is done by four HELPER warps per
+//     CTA that run ahead of the row threads; their loads are COALESCED (consecutive slots), which
+//     matters because a hand-off is paid in the polling SM's own load path (841 clocks unloaded,
+//     ~2000 with 127 scattered polls in flight, tools/micro/hop_bench.cu).  They drop each value
 //     into a shared-memory slot of the ring stage (slots arrive sentinel-filled with the static
 //     stream); a row thread therefore reads every x -- own block or not -- with one shared-memory
 //     load at a byte offset that was resolved at analysis time, and only spins (on shared memory)
@@ -43,7 +48,10 @@
 
 namespace spb {
 
-static const int WAVE_NC = 256;                          // row threads
+#ifndef SPB_WAVE_NC
+#define SPB_WAVE_NC 256
+#endif
+static const int WAVE_NC = SPB_WAVE_NC;                  // row threads
 static const int WAVE_NH = 128;                          // helper threads (cross-block values)
 static const int WAVE_HB = 4;                            // polls a helper thread keeps in flight
 static const int WAVE_THREADS = WAVE_NC + WAVE_NH + 32;  // + one producer warp
@@ -55,12 +63,13 @@ static const int WAVE_ZERO_OFF = 192;  // 16 bytes of +0.0: target of the ELL pa
 __host__ __device__ inline int wave_a16(long long v) { return (int)((v + 15) & ~15LL); }
 
 // Byte offsets of the sections of one packed chunk (all 16-byte aligned).
-// header (32 B): nrows, nseg, W, nhalo, Wo, 0, 0, 0
+// header (32 B): nrows, nseg, W, nhalo, Wo, Wm, mailbox offset (lo, hi)
+#define SPB_WAVE_NOMAIL 0xFFFFFFFFu
 struct WaveLayout {
-  int seg_end, rowid, diag, eoff, eval, hslot, hcol, total;
+  int seg_end, rowid, diag, eoff, eval, mail, hslot, total;
 };
 template <typename T>
-__host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, int nhalo) {
+__host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, int nhalo, int Wm) {
   WaveLayout L;
   int off = 32;
   L.seg_end = off;
@@ -73,10 +82,10 @@ __host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, in
   off += wave_a16(4LL * W * nrows);
   L.eval = off;
   off += wave_a16((long long)sizeof(T) * W * nrows);
-  L.hslot = off;  // sentinel-filled landing slots of the cross-block values
+  L.mail = off;  // ELL, column-major: mailbox slots (of later blocks) that want the row's value
+  off += wave_a16(4LL * Wm * nrows);
+  L.hslot = off;  // sentinel-filled landing slots of the cross-block values (mailbox order)
   off += wave_a16((long long)sizeof(T) * nhalo);
-  L.hcol = off;   // their global column ids
-  off += wave_a16(4LL * nhalo);
   L.total = off;
   return L;
 }
@@ -140,6 +149,7 @@ struct WaveArgs {
   const T* rhsp;
   const T* aux;  // null: the other triangle is skipped (sweep from zero)
   T* out;
+  T* mailbox;
   int* ticket;  // [0] block ticket, [1] timeout flag
   int nblocks, block_rows;
   int stages, stage_static, stage_rhs_bytes, stage_bytes;
@@ -148,16 +158,16 @@ struct WaveArgs {
   int gate_value;
 };
 
-// Pre-pass (fully parallel): sentinel-fill out, permute rhs into sweep order, reduce the other
+// Pre-pass (fully parallel): sentinel-fill the mailbox, permute rhs into sweep order, reduce the other
 // triangle to what the sweep needs (see the header), reset the block ticket.
 template <typename T, typename IP, bool BWD>
-__global__ void __launch_bounds__(kVecThreads) gs_wave_prep_kernel(int64_t n8, unsigned long long* out8, int64_t rhs_slots, const int* rowmap,
+__global__ void __launch_bounds__(kVecThreads) gs_wave_prep_kernel(int64_t mb8, unsigned long long* mailbox8, int64_t rhs_slots, const int* rowmap,
                                                                     const T* rhs, T* rhsp, const T* other, const IP* indptr, const int* cols,
                                                                     const T* vals, T* aux, const long long* aux_base, const int* aux_dims,
                                                                     int* ticket, const int* gate, int gate_value) {
   if (gate && *gate != gate_value) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) ticket[0] = 0;
-  SPB_GRID_STRIDE(i, n8) out8[i] = SPB_GS_SENTINEL;
+  SPB_GRID_STRIDE(i, mb8) mailbox8[i] = SPB_GS_SENTINEL;
   SPB_GRID_STRIDE(p, rhs_slots) {
     const int r = rowmap[p];
     rhsp[p] = r >= 0 ? rhs[r] : zero_of<T>();
@@ -244,21 +254,16 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
       const int* hdr = reinterpret_cast<const int*>(st);
       const int nhalo = hdr[3];
       if (nhalo > 0) {
-        const WaveLayout L = wave_layout<T>(hdr[0], hdr[1], hdr[2], nhalo);
-        const int* hcol = reinterpret_cast<const int*>(st + L.hcol);
+        const WaveLayout L = wave_layout<T>(hdr[0], hdr[1], hdr[2], nhalo, hdr[5]);
         T* hslot = reinterpret_cast<T*>(st + L.hslot);
-        for (int h0 = htid; h0 < nhalo; h0 += WAVE_NH * WAVE_HB) {  // slots are sorted by need: round-robin keeps every thread early
-          const T* src[WAVE_HB];
+        const T* mbox = a.mailbox + (((long long)hdr[7] << 32) | (unsigned)hdr[6]);  // this chunk's slots: contiguous
+        // slots are sorted by need; thread t polls slots t, t + NH, ...: coalesced, and every thread starts early
+        for (int h0 = htid; h0 < nhalo; h0 += WAVE_NH * WAVE_HB) {
           unsigned pend = 0;
-#pragma unroll
-          for (int j = 0; j < WAVE_HB; ++j) {
-            const int h = h0 + j * WAVE_NH;
-            src[j] = a.out + (h < nhalo ? hcol[h] : 0);
-          }
           T v[WAVE_HB];
 #pragma unroll
           for (int j = 0; j < WAVE_HB; ++j)
-            if (h0 + j * WAVE_NH < nhalo) v[j] = wv_poll(src[j]);
+            if (h0 + j * WAVE_NH < nhalo) v[j] = wv_poll(mbox + h0 + j * WAVE_NH);
 #pragma unroll
           for (int j = 0; j < WAVE_HB; ++j) {
             if (h0 + j * WAVE_NH < nhalo) {
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
 #pragma unroll
             for (int j = 0; j < WAVE_HB; ++j) {
               if (pend & (1u << j)) {
-                const T w = wv_poll(src[j]);
+                const T w = wv_poll(mbox + h0 + j * WAVE_NH);
                 if (!wv_is_sentinel(w)) {
                   hslot[h0 + j * WAVE_NH] = w;
                   pend &= ~(1u << j);
@@ -300,8 +305,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
     }
     const unsigned char* st = ring + (size_t)s * a.stage_bytes;
     const int* hdr = reinterpret_cast<const int*>(st);
-    const int nrows = hdr[0], nseg = hdr[1], W = hdr[2], Wo = hdr[4];
-    const WaveLayout L = wave_layout<T>(nrows, nseg, W, hdr[3]);
+    const int nrows = hdr[0], nseg = hdr[1], W = hdr[2], Wo = hdr[4], Wm = hdr[5];
+    const WaveLayout L = wave_layout<T>(nrows, nseg, W, hdr[3], Wm);
+    const uint32_t* mail = reinterpret_cast<const uint32_t*>(st + L.mail);
     const int* seg_end = reinterpret_cast<const int*>(st + L.seg_end);
     const int* rowid = reinterpret_cast<const int*>(st + L.rowid);
     const T* diag = reinterpret_cast<const T*>(st + L.diag);
@@ -339,7 +345,11 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
           for (int e = 0; e < Wo; ++e) sigma = add(sigma, auxs[e * nrows + i]);
         const T x = divi(sub(rv, sigma), dv);  // src/gauss_seidel.rs:123
         xs[row - r0] = x;
-        wv_publish(a.out + row, x);
+        for (int e = 0; e < Wm; ++e) {  // deliver to the blocks that wait for this value
+          const uint32_t m = mail[e * nrows + i];
+          if (m != SPB_WAVE_NOMAIL) wv_publish(a.mailbox + m, x);
+        }
+        a.out[row] = x;
       }
       const long long w0 = a.stats ? clock64() : 0;
       consumer_bar_sync(WAVE_NC);  // the level is complete: its x values are visible in xs
@@ -378,9 +388,24 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
     return e && *e ? atoi(e) : dflt;
   };
   ws.stages = std::max(2, std::min(WAVE_MAX_STAGES, env("SPB_GS_STAGES", 3)));
-  ws.stage_static = wave_a16(std::max(1024, env("SPB_GS_STAGE_BYTES", 16384)));
+  // Stage capacity: 16 KB holds ~256 rows of a 7-point matrix.  Fat rows (27-point: ~240 B) would
+  // leave only one or two levels per chunk and the per-chunk costs (ring hand-shake, one poll round
+  // trip of the helpers) would dominate: give them 32 KB when the x block still fits next to it.
+  int dflt_static = 16384, dflt_other = 1024;
+  {
+    const double row_bytes = 12.0 + sizeof(T) + (double)(ip[n] - n) / (double)n * 0.5 * (4.0 + sizeof(T)) * 1.15 + 16.0;
+    const int64_t need_rows = ceil_div(n, c->sm_count);
+    int smem_cap = 0;
+    SPB_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const int64_t big_stage = 32768 + wave_a16((long long)sizeof(T) * 256) + wave_a16((long long)sizeof(T) * 2048) + 128;
+    if (row_bytes > 110.0 && WAVE_FIXED + 512 + 3 * big_stage + need_rows * (int64_t)sizeof(T) <= smem_cap) {
+      dflt_static = 32768;
+      dflt_other = 2048;
+    }
+  }
+  ws.stage_static = wave_a16(std::max(1024, env("SPB_GS_STAGE_BYTES", dflt_static)));
   ws.stage_rows = std::max(8, env("SPB_GS_STAGE_ROWS", 256));
-  ws.stage_other = std::max(ws.stage_rows, env("SPB_GS_STAGE_OTHER", 1024));
+  ws.stage_other = std::max(ws.stage_rows, env("SPB_GS_STAGE_OTHER", dflt_other));
   const int rhs_bytes = wave_a16((long long)sizeof(T) * ws.stage_rows);
   const int oth_bytes = wave_a16((long long)sizeof(T) * ws.stage_other);
   const int stage_bytes = (ws.stage_static + rhs_bytes + oth_bytes + 127) / 128 * 128;
@@ -412,33 +437,6 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   rowmap.reserve((size_t)n + 2 * (size_t)nb);
   int64_t max_levels = 0, aux_slots = 0;
 
-  // per-row counts: produced entries, other-side entries, produced entries outside the block
-  std::vector<int> order, cnt;
-  struct RowInfo {
-    int np, no, nx;
-  };
-  auto row_info = [&](int64_t i, int64_t r0, int64_t r1, RowInfo& ri) {
-    ri.np = ri.no = ri.nx = 0;
-    bool seen_upper = false, okrow = true;
-    for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
-      const int j = cols[k];
-      if (j == i) continue;
-      if (j < 0 || j >= n) okrow = false;
-      if (j < i) {
-        if (seen_upper) okrow = false;  // a lower entry after an upper one: the CSR-order fold would change
-      } else {
-        seen_upper = true;
-      }
-      if (backward ? (j > i) : (j < i)) {
-        ++ri.np;
-        if (j < r0 || j >= r1) ++ri.nx;
-      } else {
-        ++ri.no;
-      }
-    }
-    return okrow;
-  };
-
   // GLOBAL levels (longest dependency chain over the whole triangle).
   {
     auto visit = [&](int64_t i) {
@@ -455,100 +453,95 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
       for (int64_t i = 0; i < n; ++i) visit(i);
   }
 
-  // open chunk
-  std::vector<int> ch_rows, ch_segend;
-  int ch_w = 0, ch_wo = 0, ch_nhalo = 0;
-  bool seg_open = false;
+  // per-row counts: produced entries, other-side entries, produced entries outside the block;
+  // ext_out[j]: how many rows of OTHER blocks read x_j (an upper bound of the mailbox slots row j
+  // delivers to -- slots are shared by the rows of one consumer chunk)
+  struct RowInfo {
+    int np, no, nx;
+  };
+  std::vector<RowInfo> rinfo(n);
+  std::vector<int> ext_out(n, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t r0 = (i / R) * R, r1 = std::min(n, r0 + R);
+    RowInfo ri{0, 0, 0};
+    bool seen_upper = false;
+    for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
+      const int j = cols[k];
+      if (j == i) continue;
+      if (j < 0 || j >= n) return;
+      if (j < i) {
+        if (seen_upper) return;  // a lower entry after an upper one: the CSR-order fold would change
+      } else {
+        seen_upper = true;
+      }
+      if (backward ? (j > i) : (j < i)) {
+        ++ri.np;
+        if (j < r0 || j >= r1) {
+          ++ri.nx;
+          ++ext_out[j];
+        }
+      } else {
+        ++ri.no;
+      }
+    }
+    rinfo[i] = ri;
+  }
 
-  auto close_chunk = [&](int64_t r0, int64_t r1, int kblk) {
-    if (ch_rows.empty()) return;
-    if (seg_open) ch_segend.push_back((int)ch_rows.size());
+  // ---- pass A: chunk membership, mailbox ranges ------------------------------------------------
+  struct Plan {
+    int row_beg, row_end;  // into plan_rows
+    int seg_beg, seg_end;  // into plan_segs
+    int hal_beg, hal_end;  // into plan_halo (distinct outside columns, in need order)
+    int W, Wo, kblk;
+    long long mb_off;
+  };
+  std::vector<Plan> plans;
+  std::vector<int> plan_rows, plan_segs, plan_halo, order, cnt;
+  plan_rows.reserve((size_t)n);
+  std::vector<int> seen(n, -1);  // seen[j] == chunk id: column j already has a slot in the open chunk
+  long long mb_total = 0;
+
+  int ch_row_beg = 0, ch_seg_beg = 0, ch_hal_beg = 0, ch_w = 0, ch_wo = 0, ch_wm_est = 0;
+  bool seg_open = false;
+  auto chunk_rows = [&]() { return (int)plan_rows.size() - ch_row_beg; };
+  auto chunk_halo = [&]() { return (int)plan_halo.size() - ch_hal_beg; };
+  auto close_chunk = [&](int kblk) {
+    if (chunk_rows() == 0) return;
+    if (seg_open) plan_segs.push_back(chunk_rows());
     seg_open = false;
-    const int nrows = (int)ch_rows.size(), nseg = (int)ch_segend.size();
-    const int W = pad4(ch_w), Wo = backward ? 0 : ch_wo;
-    const WaveLayout L = wave_layout<T>(nrows, nseg, W, ch_nhalo);
-    const size_t base = stat.size();
-    stat.resize(base + L.total, 0);
-    const uint32_t stage_base = (uint32_t)(ring_off + (size_t)(kblk % ws.stages) * stage_bytes);
-    WaveChunk d{};
-    d.soff = (long long)base;
-    d.sbytes = L.total;
-    d.nrows = nrows;
-    d.rhs_off = (long long)rowmap.size();
-    if (backward) {
-      d.aux_off = d.rhs_off;  // one pre-folded value per row, same slots as rhs
-      d.aux_cnt = nrows;
-    } else {
-      d.aux_off = aux_slots;
-      d.aux_cnt = Wo * nrows;
-      aux_slots = align_slots(aux_slots + d.aux_cnt);
+    Plan pl{ch_row_beg, (int)plan_rows.size(), ch_seg_beg, (int)plan_segs.size(), ch_hal_beg, (int)plan_halo.size(),
+            pad4(ch_w), backward ? 0 : ch_wo, kblk, mb_total};
+    mb_total = align_slots(mb_total + chunk_halo());
+    plans.push_back(pl);
+    ch_row_beg = (int)plan_rows.size();
+    ch_seg_beg = (int)plan_segs.size();
+    ch_hal_beg = (int)plan_halo.size();
+    ch_w = ch_wo = ch_wm_est = 0;
+  };
+  // distinct outside columns row i adds to the open chunk (commit: give them slots)
+  auto new_halo_of = [&](int64_t i, int64_t r0, int64_t r1, int chunk_id, bool commit) {
+    int add = 0;
+    const int mark = commit ? chunk_id : -2 - chunk_id;  // dry-run marks never equal a chunk id
+    for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
+      const int j = cols[k];
+      if (j == i || !(backward ? (j > i) : (j < i)) || (j >= r0 && j < r1)) continue;
+      if (seen[j] == chunk_id || seen[j] == mark) continue;
+      ++add;
+      seen[j] = mark;
+      if (commit) plan_halo.push_back(j);
     }
-    std::vector<uint32_t> eoff((size_t)W * nrows, (uint32_t)WAVE_ZERO_OFF);
-    std::vector<T> ev((size_t)W * nrows, zero_of<T>()), dg(nrows), hs(ch_nhalo);
-    std::vector<int> hcol(ch_nhalo);
-    for (int h = 0; h < ch_nhalo; ++h) {
-      unsigned long long w[2] = {sentinel, sentinel};
-      memcpy(&hs[h], w, sizeof(T));
-    }
-    int nh = 0;
-    for (int q = 0; q < nrows; ++q) {
-      const int64_t i = ch_rows[q];
-      int e = 0;
-      T dv = zero_of<T>();
+    if (!commit)  // undo the marks of the dry run
       for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
         const int j = cols[k];
-        if (j == i) {
-          dv = vals[k];  // the last diagonal entry wins, as in the loop of src/gauss_seidel.rs:119-121
-          continue;
-        }
-        if (!(backward ? (j > i) : (j < i))) continue;  // other triangle: handled by the pre-pass
-        uint32_t off;
-        if (j >= r0 && j < r1) {
-          off = (uint32_t)(WAVE_FIXED + (size_t)(j - r0) * sizeof(T));
-        } else {
-          hcol[nh] = j;
-          off = stage_base + (uint32_t)L.hslot + (uint32_t)(nh * sizeof(T));
-          ++nh;
-        }
-        eoff[(size_t)e * nrows + q] = off;
-        ev[(size_t)e * nrows + q] = vals[k];
-        ++e;
+        if (j >= 0 && j < n && seen[j] == mark) seen[j] = -1;
       }
-      dg[q] = dv;
-      rowmap.push_back((int)i);
-      if (!backward) {
-        aux_base.push_back(d.aux_off + q);
-        aux_dims.push_back(nrows);
-        aux_dims.push_back(Wo);
-      }
-    }
-    while ((int64_t)rowmap.size() != align_slots((int64_t)rowmap.size())) {
-      rowmap.push_back(-1);
-      if (!backward) {
-        aux_base.push_back(0);
-        aux_dims.push_back(0);
-        aux_dims.push_back(0);
-      }
-    }
-    const int hdr[8] = {nrows, nseg, W, ch_nhalo, Wo, 0, 0, 0};
-    put_bytes(stat, base, hdr, 8);
-    put_bytes(stat, base + L.seg_end, ch_segend.data(), nseg);
-    put_bytes(stat, base + L.rowid, ch_rows.data(), nrows);
-    put_bytes(stat, base + L.diag, dg.data(), nrows);
-    put_bytes(stat, base + L.eoff, eoff.data(), eoff.size());
-    put_bytes(stat, base + L.eval, ev.data(), ev.size());
-    put_bytes(stat, base + L.hslot, hs.data(), hs.size());
-    put_bytes(stat, base + L.hcol, hcol.data(), hcol.size());
-    chunks.push_back(d);
-    ch_rows.clear();
-    ch_segend.clear();
-    ch_w = ch_wo = ch_nhalo = 0;
+    return add;
   };
 
   for (int64_t t = 0; t < nb; ++t) {
     const int64_t b = backward ? nb - 1 - t : t;
     const int64_t r0 = b * R, r1 = std::min(n, r0 + R);
-    blk_chunk[t] = (int)chunks.size();
+    blk_chunk[t] = (int)plans.size();
     int minl = lev[r0], maxl = lev[r0];
     for (int64_t i = r0; i < r1; ++i) {
       minl = std::min(minl, lev[i]);
@@ -568,30 +561,137 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
     for (int l = 0; l < nl; ++l) {
       for (int q = cnt[l]; q < cnt[l + 1]; ++q) {
         const int64_t i = order[q];
-        RowInfo ri;
-        if (!row_info(i, r0, r1, ri)) return;
-        if (wave_layout<T>(1, 1, pad4(ri.np), ri.nx).total > ws.stage_static || ri.no > ws.stage_other) return;  // row too long for a stage
-        const int nr1 = (int)ch_rows.size() + 1;
-        const int nseg1 = (int)ch_segend.size() + 1;
-        const int w1 = std::max(ch_w, ri.np), wo1 = std::max(ch_wo, ri.no);
-        if (!ch_rows.empty() &&
-            (nr1 > ws.stage_rows || (!backward && (int64_t)wo1 * nr1 > ws.stage_other) ||
-             wave_layout<T>(nr1, nseg1, pad4(w1), ch_nhalo + ri.nx).total > ws.stage_static)) {
-          close_chunk(r0, r1, kblk++);
+        const RowInfo ri = rinfo[i];
+        if (wave_layout<T>(1, 1, pad4(ri.np), ri.nx, ext_out[i]).total > ws.stage_static || ri.no > ws.stage_other) return;  // row too long for a stage
+        const int nr1 = chunk_rows() + 1;
+        const int nseg1 = (int)plan_segs.size() - ch_seg_beg + 1;
+        const int w1 = std::max(ch_w, ri.np), wo1 = std::max(ch_wo, ri.no), wm1 = std::max(ch_wm_est, ext_out[i]);
+        // ri.nx over-counts the new slots when the chunk already holds some of the columns: a
+        // conservative test first, the exact count only when that one fails
+        bool fits = chunk_rows() == 0;
+        if (!fits && nr1 <= ws.stage_rows && (backward || (int64_t)wo1 * nr1 <= ws.stage_other)) {
+          fits = wave_layout<T>(nr1, nseg1, pad4(w1), chunk_halo() + ri.nx, wm1).total <= ws.stage_static;
+          if (!fits && ri.nx > 0) {
+            const int add = new_halo_of(i, r0, r1, (int)plans.size(), false);
+            fits = wave_layout<T>(nr1, nseg1, pad4(w1), chunk_halo() + add, wm1).total <= ws.stage_static;
+          }
         }
-        ch_rows.push_back((int)i);
+        if (!fits) close_chunk(kblk++);
+        new_halo_of(i, r0, r1, (int)plans.size(), true);
+        plan_rows.push_back((int)i);
         ch_w = std::max(ch_w, ri.np);
         ch_wo = std::max(ch_wo, ri.no);
-        ch_nhalo += ri.nx;
+        ch_wm_est = std::max(ch_wm_est, ext_out[i]);
         seg_open = true;
       }
       if (seg_open) {  // end of a level: barrier point
-        ch_segend.push_back((int)ch_rows.size());
+        plan_segs.push_back(chunk_rows());
         seg_open = false;
       }
     }
-    close_chunk(r0, r1, kblk++);
-    if (chunks.size() >= (size_t)1 << 31) return;
+    close_chunk(kblk++);
+    if (plans.size() >= (size_t)1 << 30) return;
+  }
+  if (mb_total >= ((long long)1 << 32) - 16) return;  // mailbox slots are addressed with 32 bits
+
+  // ---- mail lists: which slots want the value of row j ----------------------------------------
+  std::vector<int64_t> mail_ptr(n + 1, 0);
+  for (const Plan& pl : plans)
+    for (int q = pl.hal_beg; q < pl.hal_end; ++q) mail_ptr[plan_halo[q] + 1]++;
+  for (int64_t j = 0; j < n; ++j) mail_ptr[j + 1] += mail_ptr[j];
+  std::vector<uint32_t> mail_idx((size_t)mail_ptr[n]);
+  {
+    std::vector<int64_t> cur(mail_ptr.begin(), mail_ptr.end() - 1);
+    for (const Plan& pl : plans)
+      for (int q = pl.hal_beg; q < pl.hal_end; ++q) mail_idx[(size_t)cur[plan_halo[q]]++] = (uint32_t)(pl.mb_off + (q - pl.hal_beg));
+  }
+
+  // ---- pass B: emit the packed chunks ----------------------------------------------------------
+  std::vector<int> slot_of(n, -1);  // column -> slot inside the chunk being emitted
+  for (size_t ci = 0; ci < plans.size(); ++ci) {
+    const Plan& pl = plans[ci];
+    const int nrows = pl.row_end - pl.row_beg, nseg = pl.seg_end - pl.seg_beg, nhalo = pl.hal_end - pl.hal_beg;
+    const int W = pl.W, Wo = pl.Wo;
+    const int64_t first = plan_rows[pl.row_beg];
+    const int64_t r0 = (first / R) * R, r1 = std::min(n, r0 + R);
+    int Wm = 0;
+    for (int q = 0; q < nrows; ++q) {
+      const int64_t i = plan_rows[pl.row_beg + q];
+      Wm = std::max<int>(Wm, (int)(mail_ptr[i + 1] - mail_ptr[i]));
+    }
+    const WaveLayout L = wave_layout<T>(nrows, nseg, W, nhalo, Wm);
+    if (L.total > ws.stage_static) return;  // cannot happen: Wm <= the estimate used in pass A
+    const size_t base = stat.size();
+    stat.resize(base + L.total, 0);
+    const uint32_t stage_base = (uint32_t)(ring_off + (size_t)(pl.kblk % ws.stages) * stage_bytes);
+    WaveChunk d{};
+    d.soff = (long long)base;
+    d.sbytes = L.total;
+    d.nrows = nrows;
+    d.rhs_off = (long long)rowmap.size();
+    if (backward) {
+      d.aux_off = d.rhs_off;  // one pre-folded value per row, same slots as rhs
+      d.aux_cnt = nrows;
+    } else {
+      d.aux_off = aux_slots;
+      d.aux_cnt = Wo * nrows;
+      aux_slots = align_slots(aux_slots + d.aux_cnt);
+    }
+    for (int h = 0; h < nhalo; ++h) slot_of[plan_halo[pl.hal_beg + h]] = h;
+    std::vector<uint32_t> eoff((size_t)W * nrows, (uint32_t)WAVE_ZERO_OFF), mail((size_t)Wm * nrows, SPB_WAVE_NOMAIL);
+    std::vector<T> ev((size_t)W * nrows, zero_of<T>()), dg(nrows), hs(nhalo);
+    for (int h = 0; h < nhalo; ++h) {
+      unsigned long long w[2] = {sentinel, sentinel};
+      memcpy(&hs[h], w, sizeof(T));
+    }
+    for (int q = 0; q < nrows; ++q) {
+      const int64_t i = plan_rows[pl.row_beg + q];
+      int e = 0;
+      T dv = zero_of<T>();
+      for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
+        const int j = cols[k];
+        if (j == i) {
+          dv = vals[k];  // the last diagonal entry wins, as in the loop of src/gauss_seidel.rs:119-121
+          continue;
+        }
+        if (!(backward ? (j > i) : (j < i))) continue;  // other triangle: handled by the pre-pass
+        uint32_t off;
+        if (j >= r0 && j < r1)
+          off = (uint32_t)(WAVE_FIXED + (size_t)(j - r0) * sizeof(T));
+        else
+          off = stage_base + (uint32_t)L.hslot + (uint32_t)(slot_of[j] * sizeof(T));
+        eoff[(size_t)e * nrows + q] = off;
+        ev[(size_t)e * nrows + q] = vals[k];
+        ++e;
+      }
+      dg[q] = dv;
+      int m = 0;
+      for (int64_t k = mail_ptr[i]; k < mail_ptr[i + 1]; ++k) mail[(size_t)(m++) * nrows + q] = mail_idx[(size_t)k];
+      rowmap.push_back((int)i);
+      if (!backward) {
+        aux_base.push_back(d.aux_off + q);
+        aux_dims.push_back(nrows);
+        aux_dims.push_back(Wo);
+      }
+    }
+    while ((int64_t)rowmap.size() != align_slots((int64_t)rowmap.size())) {
+      rowmap.push_back(-1);
+      if (!backward) {
+        aux_base.push_back(0);
+        aux_dims.push_back(0);
+        aux_dims.push_back(0);
+      }
+    }
+    const int hdr[8] = {nrows, nseg, W, nhalo, Wo, Wm, (int)(unsigned)(pl.mb_off & 0xffffffffLL), (int)(pl.mb_off >> 32)};
+    put_bytes(stat, base, hdr, 8);
+    put_bytes(stat, base + L.seg_end, plan_segs.data() + pl.seg_beg, nseg);
+    put_bytes(stat, base + L.rowid, plan_rows.data() + pl.row_beg, nrows);
+    put_bytes(stat, base + L.diag, dg.data(), nrows);
+    put_bytes(stat, base + L.eoff, eoff.data(), eoff.size());
+    put_bytes(stat, base + L.eval, ev.data(), ev.size());
+    put_bytes(stat, base + L.mail, mail.data(), mail.size());
+    put_bytes(stat, base + L.hslot, hs.data(), hs.size());
+    chunks.push_back(d);
   }
   blk_chunk[nb] = (int)chunks.size();
   ws.nchunks = (int64_t)chunks.size();
@@ -606,6 +706,8 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   ws.rhsp.alloc(sizeof(T) * (rowmap.size() + 4));
   ws.aux.alloc(sizeof(T) * ((size_t)ws.aux_slots + 4));
   ws.ticket.alloc(sizeof(int) * 4);
+  ws.mailbox_slots = mb_total;
+  ws.mailbox.alloc(sizeof(T) * ((size_t)mb_total + 4));
   SPB_CUDA(cudaMemcpyAsync(ws.stat.p, stat.data(), stat.size(), cudaMemcpyHostToDevice, c->stream));
   SPB_CUDA(cudaMemcpyAsync(ws.chunks.p, chunks.data(), sizeof(WaveChunk) * chunks.size(), cudaMemcpyHostToDevice, c->stream));
   SPB_CUDA(cudaMemcpyAsync(ws.blk_chunk.p, blk_chunk.data(), sizeof(int) * (nb + 1), cudaMemcpyHostToDevice, c->stream));
@@ -628,11 +730,13 @@ static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* o
   Ctx* c = M->ctx;
   CsrMat<T>* A = M->A;
   const int64_t n = A->n_local;
-  const int64_t n8 = n * (int64_t)(sizeof(T) / 8);
-  const int64_t work = std::max(n8, ws.rhs_slots);
+  (void)n;
+  (void)out;
+  const int64_t mb8 = ws.mailbox_slots * (int64_t)(sizeof(T) / 8);
+  const int64_t work = std::max(mb8, ws.rhs_slots);
   LaunchScope lsc(c, FAM_PRECOND);
   auto kern = ws.backward ? gs_wave_prep_kernel<T, IP, true> : gs_wave_prep_kernel<T, IP, false>;
-  kern<<<vec_grid(c, work), kVecThreads, 0, c->stream>>>(n8, reinterpret_cast<unsigned long long*>(out), ws.rhs_slots, bufptr<int>(ws.rowmap),
+  kern<<<vec_grid(c, work), kVecThreads, 0, c->stream>>>(mb8, reinterpret_cast<unsigned long long*>(ws.mailbox.p), ws.rhs_slots, bufptr<int>(ws.rowmap),
                                                           rhs, bufptr<T>(ws.rhsp), other, bufptr<IP>(A->indptr), bufptr<int>(A->cols),
                                                           bufptr<T>(A->vals), bufptr<T>(ws.aux), bufptr<long long>(ws.aux_base),
                                                           bufptr<int>(ws.aux_dims), bufptr<int>(ws.ticket), c->gate, c->gate_value);
@@ -658,6 +762,7 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   a.rhsp = bufptr<T>(ws.rhsp);
   a.aux = other ? bufptr<T>(ws.aux) : nullptr;
   a.out = out;
+  a.mailbox = bufptr<T>(ws.mailbox);
   a.ticket = bufptr<int>(ws.ticket);
   a.nblocks = ws.nblocks;
   a.block_rows = ws.block_rows;

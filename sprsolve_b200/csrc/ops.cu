@@ -317,11 +317,12 @@ static void launch_sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T
 
 template <typename T>
 static void sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, const T* hi, T* out) {
-  // fast path: block-wavefront sweep.  It pre-fills `out`, so out must be the produced side only.
+  // fast path: block-wavefront sweep (the produced side must be the vector being written; rhs and
+  // the other triangle are consumed by its pre-pass, so out may alias them)
   const bool fwd = &ls == &M->fwd;
   WaveSched& ws = fwd ? M->wfwd : M->wbwd;
   const T* other = fwd ? hi : lo;
-  if (ws.ok && (fwd ? lo : hi) == out && out != rhs && out != other) {
+  if (ws.ok && (fwd ? lo : hi) == out) {
     wave_sweep<T>(M, ws, rhs, other, out);
     return;
   }

@@ -54,6 +54,8 @@ struct WaveSched {
   DevBuf aux_dims;   // int32 [2 * rhs_slots] (forward only): stride (rows of the chunk), Wo
   DevBuf rhsp;       // T [rhs_slots]  (per apply)
   DevBuf aux;        // T [aux_slots]  (per apply)
+  DevBuf mailbox;    // T [mailbox_slots]: cross-block values, one contiguous slot range per consumer chunk (per apply)
+  int64_t mailbox_slots = 0;
   DevBuf ticket;     // int32 [4]: block ticket, timeout flag
 };
 
@@ -91,7 +93,7 @@ void gs_solver_sweep(GsOp<T>* M, const T* rhs, const T* x_old, T* x_new);
 
 // gs_wave.cu: block-wavefront sweep.  wave_build analyses one direction (host CSR copy in);
 // wave_sweep runs out = sweep(rhs) where the produced side reads `out` itself and the other
-// triangle reads `other` (null: skipped, i.e. a sweep from zero).  out must not alias rhs/other.
+// triangle reads `other` (null: skipped, i.e. a sweep from zero).  out may alias rhs / other.
 template <typename T>
 void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<int>& cols,
                 const std::vector<T>& vals, bool backward, WaveSched& ws);
