@@ -49,6 +49,15 @@ extern "C" {
         indptr: *const c_void, indptr_bits: c_int, indices: *const i32, values: *const c_void,
         out: *mut *mut spb_op,
     ) -> c_int;
+    pub fn spb_csc_create(
+        ctx: *mut spb_ctx, dtype: c_int, nrows: i64, ncols: i64, indptr: *const c_void, indptr_bits: c_int,
+        row_indices: *const i32, values: *const c_void, out: *mut *mut spb_op,
+    ) -> c_int;
+    pub fn spb_csr_create_from_triplets(
+        ctx: *mut spb_ctx, dtype: c_int, nrows: i64, ncols: i64, nnz: i64, rows: *const i32, cols: *const i32,
+        values: *const c_void, out: *mut *mut spb_op,
+    ) -> c_int;
+    pub fn spb_csr_read_matrix_market(ctx: *mut spb_ctx, dtype: c_int, path: *const c_char, out: *mut *mut spb_op) -> c_int;
     pub fn spb_csr_mv_hint(mat: *mut spb_op, ncalls: c_int) -> c_int;
     pub fn spb_csr_mv_and_dotmv_hint(mat: *mut spb_op, ncalls: c_int) -> c_int;
     pub fn spb_op_destroy(op: *mut spb_op) -> c_int;
@@ -142,6 +151,37 @@ impl<'c, T: GpuScalar> GpuCsrMat<'c, T> {
             return Err(st as u32);
         }
         Ok(GpuCsrMat { h, size: nrow, _ctx: PhantomData, _t: PhantomData })
+    }
+    /// A CSC matrix as the operator: the CSC branch of `CsMatViewI::mul_vec` (src/mat.rs:130-142).
+    /// Transposed on the device with a stable sort, so `mul_vec` keeps the accumulation order of
+    /// the reference's column-by-column loop.
+    pub fn from_csc(ctx: &'c GpuContext, m: CsMatI<T, i32>) -> Result<Self, u32> {
+        assert!(m.is_csc());
+        let (nrow, ncol) = (m.rows(), m.cols());
+        let (indptr, indices, data) = m.into_raw_storage();
+        let mut h = std::ptr::null_mut();
+        let st = unsafe {
+            spb_csc_create(ctx.h, T::DTYPE, nrow as i64, ncol as i64, indptr.as_ptr() as *const c_void, 32,
+                           indices.as_ptr(), data.as_ptr() as *const c_void, &mut h)
+        };
+        if st != SPB_OK {
+            return Err(st as u32);
+        }
+        Ok(GpuCsrMat { h, size: nrow, _ctx: PhantomData, _t: PhantomData })
+    }
+    /// `sprs::TriMat::to_csr` on the device (the reference's fixtures: tests/test_minres.rs:65-119):
+    /// sorted by (row, column), duplicates summed in input order.
+    pub fn from_triplets(ctx: &'c GpuContext, n: usize, rows: &[i32], cols: &[i32], data: &[T]) -> Result<Self, u32> {
+        assert!(rows.len() == cols.len() && cols.len() == data.len());
+        let mut h = std::ptr::null_mut();
+        let st = unsafe {
+            spb_csr_create_from_triplets(ctx.h, T::DTYPE, n as i64, n as i64, rows.len() as i64, rows.as_ptr(),
+                                         cols.as_ptr(), data.as_ptr() as *const c_void, &mut h)
+        };
+        if st != SPB_OK {
+            return Err(st as u32);
+        }
+        Ok(GpuCsrMat { h, size: n, _ctx: PhantomData, _t: PhantomData })
     }
     /// `MklMat::size` (src/mkl_mat.rs:26-28)
     #[inline(always)]
