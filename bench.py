@@ -347,14 +347,24 @@ def run_gpu(args):
     n_products = 2 * iters + 1
     avg_ms = max_over_ranks(ms_spmv / n_products)
     achieved = b_spmv / (avg_ms * 1e-3) / 1e9
+    # What the analysis chose for this matrix.  With the column-offset dictionary the kernel streams
+    # 8 instead of 12 bytes per non-zero, so the ALGORITHMIC figure (the bytes of the reference's CSR
+    # operator) can exceed the HBM peak; `stream_*` are the bytes the kernel
+    # moves by design, which is what the HBM roofline bounds.
+    plan = A.plan_info()
+    stream = plan["stream_bytes"]
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_spmv512_ncu_full.json")
+    tp = os.path.join(ROOT, "profiles", "r01_spmv512_dict_ncu_full.json" if plan["dictionary"] else "r01_spmv512_ncu_full.json")
     if world == 1 and g == 512 and os.path.exists(tp):
         traffic = float(json.load(open(tp))["traffic_bytes_per_launch"])
-        traffic_src = "profiles/r01_spmv512_ncu_full.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, same workload)"
+        traffic_src = f"profiles/{os.path.basename(tp)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, same workload)"
     roofline = {
         "bound": "hbm", "kernel": "spmv_tma_kernel<double> (CSR SpMV, 27-pt, this rank's rows)", "achieved": achieved, "peak": peak,
         "unit": "GB/s (per GPU)", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "format": (f"CSR values + 16-bit row-pattern ids ({plan['patterns']} column-offset patterns found by the analysis)"
+                   if plan["dictionary"] else "CSR values + int32 column indices"),
+        "stream_bytes_per_launch": stream, "stream_gbs": stream / (avg_ms * 1e-3) / 1e9, "stream_frac": stream / (avg_ms * 1e-3) / 1e9 / peak,
+        "plan": {k: plan[k] for k in ("consumer_threads", "stages", "tile_nnz", "ctas_per_sm")},
         "bytes_per_launch": b_spmv, "avg_launch_ms": avg_ms, "launches_timed": n_spmv, "products_timed": n_products,
         "step_share": {"spmv_ms": ms_spmv, "vector_ms": ms_vec, "scalar_ms": ms_sc, "spmv_launches": n_spmv, "vector_launches": n_vec, "scalar_launches": n_sc},
         "iteration_bytes_model": 2 * b_spmv + 21 * n_loc * 8,

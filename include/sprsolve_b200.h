@@ -124,6 +124,10 @@ int spb_csr_mv_and_dotmv_hint(spb_op* mat, int ncalls);
 /* MklMat::size (src/mkl_mat.rs:26-28), plus local sizes for partitioned matrices. */
 int spb_op_size(spb_op* op, int64_t* n_global, int64_t* n_local, int64_t* row_begin);
 int spb_csr_nnz(spb_op* mat, int64_t* nnz_local);
+/* What the analysis (the mkl_sparse_optimize analogue, src/mkl_mat.rs:104-121) decided for this matrix:
+ * info = {column-offset dictionary on, distinct row patterns, dictionary row stride, consumer threads per CTA,
+ * ring stages, non-zeros per tile, resident CTAs per SM, bytes one mul_vec streams from HBM by design}. */
+int spb_csr_plan_info(spb_op* mat, int64_t info[8]);
 /* Copy the local CSR arrays back (tests / generators parity).  indptr64 has n_local+1 entries. */
 int spb_csr_download(spb_op* mat, int64_t* indptr64, int32_t* indices_global, void* values);
 /* diag[i] = a_ii (0 when absent) of the local rows, host buffer of n_local T. */

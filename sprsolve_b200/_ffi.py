@@ -53,6 +53,7 @@ SIGNATURES = {
     "spb_stencil_partition": (C.c_int, [C.c_int, i64, i64, i64, C.c_int, C.c_int, pi64, pi64]),
     "spb_csr_create": (C.c_int, [vp, C.c_int, i64, i64, i64, i64, vp, C.c_int, vp, vp, pp]),
     "spb_csr_create_stencil": (C.c_int, [vp, C.c_int, C.c_int, i64, i64, i64, pdbl, C.c_int, pp]),
+    "spb_csr_plan_info": (C.c_int, [vp, pi64]),
     "spb_csc_create": (C.c_int, [vp, C.c_int, i64, i64, vp, C.c_int, vp, vp, pp]),
     "spb_csr_create_from_triplets": (C.c_int, [vp, C.c_int, i64, i64, i64, vp, vp, vp, pp]),
     "spb_csr_read_matrix_market": (C.c_int, [vp, C.c_int, C.c_char_p, pp]),

@@ -359,6 +359,13 @@ class GpuCsrMat(MatVecMul):
         _check(F.lib().spb_csr_nnz(self._h, C.byref(v)))
         return int(v.value)
 
+    def plan_info(self) -> dict:
+        """What the analysis decided (spb_csr_plan_info)."""
+        v = (C.c_int64 * 8)()
+        _check(F.lib().spb_csr_plan_info(self._h, v))
+        keys = ["dictionary", "patterns", "dict_width", "consumer_threads", "stages", "tile_nnz", "ctas_per_sm", "stream_bytes"]
+        return {k: int(v[i]) for i, k in enumerate(keys)}
+
     def download(self):
         """(indptr int64, indices int32 global, data) of the local rows."""
         n, nnz = self.n_local, self.nnz

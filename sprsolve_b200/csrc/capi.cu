@@ -383,6 +383,30 @@ static void csr_download(CsrMat<T>* m, int64_t* indptr64, int32_t* indices, void
   }
 }
 
+namespace {
+template <typename T>
+void csr_plan_info_impl(spb_op* op, int64_t* info) {
+  auto* m = static_cast<CsrMat<T>*>(op);
+  const int64_t ipb = m->ip64 ? 8 : 4, vb = (int64_t)sizeof(T);
+  // bytes one mul_vec streams from HBM by design: values (+ column indices unless the pattern
+  // dictionary replaces them by a 16-bit id per row) + row pointers + x once + y once
+  const int64_t stream = m->nnz * (vb + (m->dict_on ? 0 : 4)) + (m->n_local + 1) * ipb + (m->dict_on ? 2 * m->n_local : 0) + 2 * m->n_local * vb;
+  const int64_t v[8] = {m->dict_on ? 1 : 0, m->dict_u, m->dict_w, m->plan_ct, m->plan_stages, m->plan_tile, m->plan_bps, stream};
+  for (int i = 0; i < 8; ++i) info[i] = v[i];
+}
+}  // namespace
+
+int spb_csr_plan_info(spb_op* m, int64_t info[8]) {
+  SPB_TRY
+  SPB_REQUIRE(m && m->kind == OP_CSR && info, "not a CSR matrix");
+  if (m->dtype == SPB_F64)
+    csr_plan_info_impl<double>(m, info);
+  else
+    csr_plan_info_impl<cplx>(m, info);
+  return SPB_OK;
+  SPB_CATCH
+}
+
 int spb_csr_download(spb_op* m, int64_t* indptr64, int32_t* indices, void* values) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR, "not a CSR matrix");

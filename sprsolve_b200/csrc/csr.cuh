@@ -54,6 +54,13 @@ struct CsrMat : spb_op {
   DevBuf partials;       // T [2 * max grid], per-block epilogue partial sums
   DevBuf red;            // scal2[2]: finalised epilogue sums
 
+  // --- column-offset dictionary (stencil-like matrices; spmv.cu) ---------------------------
+  bool dict_on = false;
+  int dict_w = 0;        // dictionary row stride = longest row
+  int64_t dict_u = 0;    // number of distinct row patterns
+  DevBuf dict_off;       // int32 [dict_u * dict_w]: col - row of the pattern's entries
+  DevBuf pid;            // uint16 [n_local]: pattern id of every row
+
   // --- row-block partition (multi-GPU) ------------------------------------------------------
   int64_t n_halo = 0;
   DevBuf halo;               // T [n_halo]: remote x entries, grouped by owner rank

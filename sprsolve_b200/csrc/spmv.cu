@@ -70,6 +70,10 @@ struct SpmvArgs {
   HaloHead* hhead;
   long long halo_stride;
   long long first_boundary;
+  // column-offset dictionary (DICT kernels): row r has columns r + doff[pid[r] * dict_w + k]
+  const unsigned short* pid;
+  const int* doff;
+  int dict_w;
 };
 
 // x entry for local column id c.  Single GPU (HALO = false): every column is owned.  Partitioned
@@ -135,13 +139,13 @@ __device__ __forceinline__ void row_range(const SpmvArgs<T, IP>& a, const TileMe
 }
 
 // blockDim.x = CT consumer threads + one producer warp.
-template <typename T, typename IP, bool HALO, int EPI, bool CONJ_IN>
+template <typename T, typename IP, bool HALO, int EPI, bool CONJ_IN, bool DICT>
 __global__ void __launch_bounds__(288)
 spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int CT = (int)blockDim.x - 32;
   const int VAL_BYTES = align16i((a.tile + 4) * (int)sizeof(T));
-  const int COL_BYTES = align16i((a.tile + 4) * 4);
+  const int COL_BYTES = DICT ? 0 : align16i((a.tile + 4) * 4);  // DICT: the column stream is not read at all
   const int IP_BYTES = align16i((a.rcap + 8) * (int)sizeof(IP));
   const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES;  // vals | cols | indptr slice
   const int STAGES = a.stages;
@@ -208,12 +212,12 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           m.ip_off = ip_ok ? (r0 - ra) : -1;
           meta[s] = m;
           const uint32_t groups = (uint32_t)((m.total + 3) >> 2);
-          const uint32_t bytes = groups * (16u + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u);
+          const uint32_t bytes = groups * ((DICT ? 0u : 16u) + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u);
           if (bytes) {
             mbar_arrive_expect_tx(&full[s], bytes);
             if (groups) {
               bulk_g2s(stage, a.vals + s4, groups * 4u * (uint32_t)sizeof(T), &full[s], pol_stream);
-              bulk_g2s(stage + VAL_BYTES, a.cols + s4, groups * 16u, &full[s], pol_stream);
+              if (!DICT) bulk_g2s(stage + VAL_BYTES, a.cols + s4, groups * 16u, &full[s], pol_stream);
             }
             if (ip_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES, a.indptr + ra, (uint32_t)nip * (uint32_t)sizeof(IP), &full[s], pol_stream);
           } else {
@@ -255,11 +259,23 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           row_range(a, m, s_ip, r, p0, p1);
           T acc = zero_of<T>();
           int k = p0;
+          // DICT: the row's column offsets come from the pattern dictionary (a few KB, L1 resident;
+          // neighbouring rows share the pattern, so the loads of a warp are broadcasts)
+          // (dict_w is a multiple of 8 and padded with zero offsets: two 16-byte loads per batch,
+          // also for the partial batch at the end of a row -- a padding entry gathers x[r])
+          const int4* dp = DICT ? reinterpret_cast<const int4*>(a.doff + (int)a.pid[r] * a.dict_w) : nullptr;
           for (; k + 8 <= p1; k += 8) {
             int c[8];
             T xv[8];
+            if (DICT) {
+              const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+              dp += 2;
+              c[0] = r + q0.x; c[1] = r + q0.y; c[2] = r + q0.z; c[3] = r + q0.w;
+              c[4] = r + q1.x; c[5] = r + q1.y; c[6] = r + q1.z; c[7] = r + q1.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) c[j] = s_col[k + j];
+              for (int j = 0; j < 8; ++j) c[j] = s_col[k + j];
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HALO>(xb, xh_adj, nl, c[j], pol_x);
 #pragma unroll
@@ -268,8 +284,14 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           if (k < p1) {
             int c[8];
             T xv[8];
+            if (DICT) {
+              const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+              c[0] = r + q0.x; c[1] = r + q0.y; c[2] = r + q0.z; c[3] = r + q0.w;
+              c[4] = r + q1.x; c[5] = r + q1.y; c[6] = r + q1.z; c[7] = r + q1.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) c[j] = s_col[min(k + j, p1 - 1)];
+              for (int j = 0; j < 8; ++j) c[j] = s_col[min(k + j, p1 - 1)];
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HALO>(xb, xh_adj, nl, c[j], pol_x);
 #pragma unroll
@@ -379,32 +401,170 @@ __global__ void finalize_partials_kernel(const T* partials, int64_t nblocks, sca
   if (threadIdx.x < 2) red[threadIdx.x] = scal2{loc[2 * threadIdx.x], loc[2 * threadIdx.x + 1]};
 }
 
+// ---------------------------------------------------------------- column-offset dictionary
+// The part of the mkl_sparse_optimize analogue that shrinks the matrix stream: rows whose column
+// offsets (col - row, in CSR order) coincide share a PATTERN.  A stencil-like matrix has a handful
+// of patterns (27-point 512^3: one per combination of touched domain faces), so per row a 16-bit
+// pattern id replaces nnz_row * 4 bytes of column indices -- the SpMV then streams 8 instead of 12
+// bytes per non-zero (f64) and is bit-identical (same entries, same order).  Everything runs on the
+// device (the 512^3 matrix never exists on the host): hash every row, stable radix sort of
+// (hash, row), run heads -> pattern ids, a representative row per pattern fills the dictionary,
+// and a verification pass compares every row with its dictionary entry (a hash collision, or too
+// many / too long patterns, simply leaves the dictionary off).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long h, unsigned long long v) {
+  h ^= v + 0x9E3779B97F4A7C15ULL + (h << 6) + (h >> 2);
+  h *= 0xBF58476D1CE4E5B9ULL;
+  return h ^ (h >> 29);
+}
+template <typename IP>
+__global__ void dict_hash_kernel(const IP* indptr, const int* cols, int64_t n, unsigned long long* keys, int* rows) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const IP p0 = indptr[r], p1 = indptr[r + 1];
+    unsigned long long h = mix64(0x1234567ULL, (unsigned long long)(p1 - p0));
+    for (IP k = p0; k < p1; ++k) h = mix64(h, (unsigned long long)(unsigned)(cols[k] - (int)r));
+    keys[r] = h;
+    rows[r] = (int)r;
+  }
+}
+__global__ void dict_heads_kernel(const unsigned long long* keys, int64_t n, int* head) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    head[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
+}
+// head / run: flags and their exclusive scan over the sorted order
+template <typename IP>
+__global__ void dict_fill_kernel(const IP* indptr, const int* cols, const int* rows_sorted, const int* head, const int* run, int64_t n,
+                                 int w, int* doff, int* dlen, unsigned short* pid) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = rows_sorted[i];
+    const int u = run[i] + head[i] - 1;  // index of the run this row belongs to
+    pid[r] = (unsigned short)u;
+    if (head[i]) {  // representative of its pattern
+      const IP p0 = indptr[r], p1 = indptr[r + 1];
+      dlen[u] = (int)(p1 - p0);
+      for (IP k = p0; k < p1; ++k) doff[(int64_t)u * w + (k - p0)] = cols[k] - r;
+    }
+  }
+}
+template <typename IP>
+__global__ void dict_verify_kernel(const IP* indptr, const int* cols, int64_t n, int w, const int* doff, const int* dlen,
+                                   const unsigned short* pid, int* bad) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const IP p0 = indptr[r], p1 = indptr[r + 1];
+    const int u = pid[r];
+    bool ok = dlen[u] == (int)(p1 - p0);
+    for (IP k = p0; ok && k < p1; ++k) ok = doff[(int64_t)u * w + (k - p0)] == cols[k] - (int)r;
+    if (!ok) atomicExch(bad, 1);
+  }
+}
+
+template <typename T, typename IP>
+static void build_dict_impl(CsrMat<T>* m) {
+  Ctx* c = m->ctx;
+  const int64_t n = m->n_local;
+  m->dict_on = false;
+  const char* e = getenv("SPB_SPMV_DICT");
+  if ((e && *e == '0') || n <= 0 || n >= ((int64_t)1 << 31) - 1 || m->max_row > 64 || m->max_row < 1) return;
+  // Measured (profiles/r01_spmv_dict.txt): pays when the column stream is a third of the bytes and
+  // rows are long (27-point f64: 1.24x); 7-point rows and complex values (4 of 20 bytes) gain
+  // nothing -- their kernels are bound by the x gathers -- so they keep the plain stream.
+  if (!(e && *e == '1') && (sizeof(T) != 8 || (double)m->nnz < 12.0 * (double)n)) return;
+  const int w = ((int)m->max_row + 7) & ~7;  // 8 offsets = two 16-byte loads per gather batch
+  DevBuf keys, keys2, rows, rows2, head, run, tmp, bad;
+  keys.alloc(8 * (size_t)n);
+  keys2.alloc(8 * (size_t)n);
+  rows.alloc(4 * (size_t)n);
+  rows2.alloc(4 * (size_t)n);
+  head.alloc(4 * (size_t)n);
+  run.alloc(4 * (size_t)n);
+  bad.alloc(16);
+  SPB_CUDA(cudaMemsetAsync(bad.p, 0, 16, c->stream));
+  const int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)c->sm_count * 16);
+  const IP* ip = bufptr<IP>(m->indptr);
+  const int* cols = bufptr<int>(m->cols);
+  {
+    LaunchScope ls(c, FAM_SCALAR);
+    dict_hash_kernel<IP><<<grid, 256, 0, c->stream>>>(ip, cols, n, keys.as<unsigned long long>(), rows.as<int>());
+    check_launch("dict_hash_kernel");
+  }
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), rows.as<int>(), rows2.as<int>(),
+                                  (int)n, 0, 64, c->stream);
+  tmp.alloc(tb);
+  {
+    LaunchScope ls(c, FAM_SCALAR);
+    SPB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.as<unsigned long long>(), keys2.as<unsigned long long>(), rows.as<int>(),
+                                             rows2.as<int>(), (int)n, 0, 64, c->stream));
+    dict_heads_kernel<<<grid, 256, 0, c->stream>>>(keys2.as<unsigned long long>(), n, head.as<int>());
+    check_launch("dict_heads_kernel");
+  }
+  size_t tb2 = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb2, head.as<int>(), run.as<int>(), (int)n, c->stream);
+  tmp.ensure(tb2);
+  {
+    LaunchScope ls(c, FAM_SCALAR);
+    SPB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, head.as<int>(), run.as<int>(), (int)n, c->stream));
+  }
+  int last_run = 0, last_head = 0;
+  SPB_CUDA(cudaMemcpyAsync(&last_run, run.as<int>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  SPB_CUDA(cudaMemcpyAsync(&last_head, head.as<int>() + (n - 1), 4, cudaMemcpyDeviceToHost, c->stream));
+  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  const int64_t u = (int64_t)last_run + last_head;
+  if (u > 65535 || u * w > (1 << 18)) return;  // not a stencil-like matrix: keep the plain column stream
+  DevBuf doff, dlen, pid;
+  doff.alloc(sizeof(int) * (size_t)(u * w + 64));
+  dlen.alloc(sizeof(int) * (size_t)u);
+  pid.alloc(sizeof(unsigned short) * (size_t)n + 16);
+  SPB_CUDA(cudaMemsetAsync(doff.p, 0, doff.bytes, c->stream));
+  {
+    LaunchScope ls(c, FAM_SCALAR);
+    dict_fill_kernel<IP><<<grid, 256, 0, c->stream>>>(ip, cols, rows2.as<int>(), head.as<int>(), run.as<int>(), n, w, doff.as<int>(),
+                                                      dlen.as<int>(), pid.as<unsigned short>());
+    dict_verify_kernel<IP><<<grid, 256, 0, c->stream>>>(ip, cols, n, w, doff.as<int>(), dlen.as<int>(), pid.as<unsigned short>(),
+                                                        bad.as<int>());
+    check_launch("dict_verify_kernel");
+  }
+  int isbad = 0;
+  SPB_CUDA(cudaMemcpyAsync(&isbad, bad.p, 4, cudaMemcpyDeviceToHost, c->stream));
+  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  if (isbad) return;  // hash collision: two different rows in one run
+  m->dict_off = std::move(doff);
+  m->pid = std::move(pid);
+  m->dict_w = w;
+  m->dict_u = u;
+  m->dict_on = true;
+}
+
 // ---------------------------------------------------------------- launch plumbing
 template <typename T, typename IP>
 static size_t spmv_smem_bytes(const CsrMat<T>* m) {
-  const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + align16i((m->plan_tile + 4) * 4) +
+  const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + (m->dict_on ? 0 : align16i((m->plan_tile + 4) * 4)) +
                        align16i((m->plan_rcap + 8) * (int)sizeof(IP));
   return m->plan_stages * stage + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(T) + 32;
 }
 
 // Runs f(kernel_pointer) for the kernel instance selected by (halo, epi, conj).
-template <typename T, typename IP, bool HALO, typename F>
+template <typename T, typename IP, bool HALO, bool DICT, typename F>
 static void with_kernel_ax(int epi, bool conj_in, F&& f) {
   constexpr bool CZ = ScalarTraits<T>::is_complex;
   if (CZ && conj_in) {
-    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, HALO, EPI_NONE, CZ>);
-    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, HALO, EPI_DOT_WY, CZ>);
-    else f(spmv_tma_kernel<T, IP, HALO, EPI_TT_TR, CZ>);
+    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, HALO, EPI_NONE, CZ, DICT>);
+    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, HALO, EPI_DOT_WY, CZ, DICT>);
+    else f(spmv_tma_kernel<T, IP, HALO, EPI_TT_TR, CZ, DICT>);
   } else {
-    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, HALO, EPI_NONE, false>);
-    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, HALO, EPI_DOT_WY, false>);
-    else f(spmv_tma_kernel<T, IP, HALO, EPI_TT_TR, false>);
+    if (epi == EPI_NONE) f(spmv_tma_kernel<T, IP, HALO, EPI_NONE, false, DICT>);
+    else if (epi == EPI_DOT_WY) f(spmv_tma_kernel<T, IP, HALO, EPI_DOT_WY, false, DICT>);
+    else f(spmv_tma_kernel<T, IP, HALO, EPI_TT_TR, false, DICT>);
   }
 }
 template <typename T, typename IP, typename F>
-static void with_kernel(int halo, int epi, bool conj_in, F&& f) {
-  if (halo) with_kernel_ax<T, IP, true>(epi, conj_in, f);
-  else with_kernel_ax<T, IP, false>(epi, conj_in, f);
+static void with_kernel(int halo, bool dict, int epi, bool conj_in, F&& f) {
+  if (halo) {
+    if (dict) with_kernel_ax<T, IP, true, true>(epi, conj_in, f);
+    else with_kernel_ax<T, IP, true, false>(epi, conj_in, f);
+  } else {
+    if (dict) with_kernel_ax<T, IP, false, true>(epi, conj_in, f);
+    else with_kernel_ax<T, IP, false, false>(epi, conj_in, f);
+  }
 }
 
 template <typename T, typename IP>
@@ -412,7 +572,7 @@ static void launch_spmv(CsrMat<T>* m, const SpmvArgs<T, IP>& args, int epi, bool
   Ctx* ctx = m->ctx;
   LaunchScope ls(ctx, FAM_SPMV);
   const size_t smem = spmv_smem_bytes<T, IP>(m);
-  with_kernel<T, IP>(m->n_halo > 0 ? 1 : 0, epi, conj_in, [&](auto kernel) {
+  with_kernel<T, IP>(m->n_halo > 0 ? 1 : 0, m->dict_on, epi, conj_in, [&](auto kernel) {
     SPB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, m->plan_ct + 32, smem, ctx->stream>>>(args);
   });
@@ -423,7 +583,7 @@ template <typename T, typename IP>
 static int spmv_blocks_per_sm(CsrMat<T>* m) {
   int nb = 0;
   const size_t smem = spmv_smem_bytes<T, IP>(m);
-  with_kernel<T, IP>(m->n_halo > 0 ? 1 : 0, EPI_TT_TR, false, [&](auto kernel) {
+  with_kernel<T, IP>(m->n_halo > 0 ? 1 : 0, m->dict_on, EPI_TT_TR, false, [&](auto kernel) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, m->plan_ct + 32, smem);
   });
@@ -465,13 +625,17 @@ void CsrMat<T>::analyze() {
   // ~21 KB per stage is the sweet spot; rows of <= 12 non-zeros want a 2-stage ring (the row
   // phase is short, the bulk-copy latency dominates), longer rows want 1 stage and twice the
   // resident CTAs (the row phase dominates).
+  if (ip64)
+    build_dict_impl<T, int64_t>(this);
+  else
+    build_dict_impl<T, int32_t>(this);
   const double mean = n_local > 0 ? (double)nnz / (double)n_local : 0.0;
   const int mean_c = (int)std::max(1.0, std::ceil(mean));
-  const int bytes_per_nnz = (int)sizeof(T) + 4;
+  const int bytes_per_nnz = (int)sizeof(T) + (dict_on ? 0 : 4);
   int ct = env_int("SPB_SPMV_CT", 0);
   if (ct <= 0) ct = (int)((21504 / ((int64_t)mean_c * bytes_per_nnz)) / 32 * 32);
   int stages = env_int("SPB_SPMV_STAGES", 0);
-  if (stages <= 0) stages = mean <= 12.0 ? 2 : 1;
+  if (stages <= 0) stages = mean <= 12.0 ? 2 : 1;  // (also the best choice for the dictionary kernel: profiles/r01_spmv_dict.txt)
   build_plan(ct, stages);
   partials.alloc(sizeof(T) * 2 * (size_t)(2 * (int64_t)c->sm_count * 32 + 2));
   red.alloc(sizeof(scal2) * 2);
@@ -490,7 +654,7 @@ void CsrMat<T>::build_plan(int ct, int stages) {
   const int rpt = std::max(1, env_int("SPB_SPMV_RPT", 1));
   const int64_t row_extra = std::min<int64_t>(max_row, 4096);
   plan_ct = std::max(32, std::min(256, ct / 32 * 32));
-  auto stage_bytes = [&](int64_t tile) { return (tile + 4) * (int64_t)(sizeof(T) + 4) + (2 * 256 + 16) * (int64_t)sizeof(int64_t); };
+  auto stage_bytes = [&](int64_t tile) { return (tile + 4) * (int64_t)(sizeof(T) + (dict_on ? 0 : 4)) + (2 * 256 + 16) * (int64_t)sizeof(int64_t); };
   int64_t tile = std::max<int64_t>(256, (((int64_t)plan_ct * rpt * mean_c + row_extra) + 3) & ~3LL);
   const int64_t hard_cap = 200 * 1024;  // one CTA must fit
   while (plan_stages > 1 && plan_stages * stage_bytes(tile) > hard_cap) --plan_stages;
@@ -583,13 +747,15 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
       SpmvArgs<T, int64_t> a{bufptr<int64_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
-                             plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary};
+                             plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
+                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w};
       launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
       SpmvArgs<T, int32_t> a{bufptr<int32_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
-                             plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary};
+                             plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
+                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w};
       launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
     }
     return grid;
