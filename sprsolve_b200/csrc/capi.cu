@@ -599,12 +599,12 @@ int spb_gs_levels(spb_op* gs, int64_t* nf, int64_t* nb) {
   SPB_REQUIRE(gs && gs->kind == OP_GS, "not a Gauss-Seidel operator");
   if (gs->dtype == SPB_F64) {
     auto* g = static_cast<GsOp<double>*>(gs);
-    if (nf) *nf = g->fwd.nlevels;
-    if (nb) *nb = g->bwd.nlevels;
+    if (nf) *nf = g->wfwd.ok ? g->wfwd.global_levels : g->fwd.nlevels;
+    if (nb) *nb = g->wbwd.ok ? g->wbwd.global_levels : g->bwd.nlevels;
   } else {
     auto* g = static_cast<GsOp<cplx>*>(gs);
-    if (nf) *nf = g->fwd.nlevels;
-    if (nb) *nb = g->bwd.nlevels;
+    if (nf) *nf = g->wfwd.ok ? g->wfwd.global_levels : g->fwd.nlevels;
+    if (nb) *nb = g->wbwd.ok ? g->wbwd.global_levels : g->bwd.nlevels;
   }
   return SPB_OK;
   SPB_CATCH

@@ -451,6 +451,9 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
       for (int64_t i = n - 1; i >= 0; --i) visit(i);
     else
       for (int64_t i = 0; i < n; ++i) visit(i);
+    int gl = 0;
+    for (int64_t i = 0; i < n; ++i) gl = std::max(gl, lev[i]);
+    ws.global_levels = (int64_t)gl + 1;
   }
 
   // per-row counts: produced entries, other-side entries, produced entries outside the block;

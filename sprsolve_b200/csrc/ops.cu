@@ -7,6 +7,7 @@
 // walks all levels with a grid-wide barrier in between (no kernel launch per level).
 #include <algorithm>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "ops.cuh"
@@ -270,24 +271,74 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
     if (A->nnz) SPB_CUDA(cudaMemcpyAsync(cols.data(), A->cols.p, sizeof(int) * A->nnz, cudaMemcpyDeviceToHost, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
     op->bad_row = bad == ~0ULL ? -1 : (int64_t)bad;
-    build_levels(c, n, ip, cols, true, op->fwd);
-    build_levels(c, n, ip, cols, false, op->bwd);
-    {  // block-wavefront schedules (gs_wave.cu) -- the fast path
+    {  // block-wavefront schedules (gs_wave.cu) -- the fast path.  The two directions are independent
+       // host analyses of the same pattern: a second thread builds the backward one.
       std::vector<T> vals((size_t)A->nnz);
       if (A->nnz) SPB_CUDA(cudaMemcpyAsync(vals.data(), A->vals.p, sizeof(T) * A->nnz, cudaMemcpyDeviceToHost, c->stream));
       SPB_CUDA(cudaStreamSynchronize(c->stream));
-      wave_build<T>(A, ip, cols, vals, false, op->wfwd);
-      if (mode == SPB_GS_SYMMETRIC) wave_build<T>(A, ip, cols, vals, true, op->wbwd);
+      int bwd_status = SPB_OK;
+      std::thread bwd_thread;
+      if (mode == SPB_GS_SYMMETRIC)
+        bwd_thread = std::thread([&]() {
+          try {
+            SPB_CUDA(cudaSetDevice(c->device));
+            wave_build<T>(A, ip, cols, vals, true, op->wbwd);
+          } catch (const SpbError& e) {
+            bwd_status = e.status;
+          } catch (...) {
+            bwd_status = SPB_CUDA_ERROR;
+          }
+        });
+      int fwd_status = SPB_OK;
+      try {
+        wave_build<T>(A, ip, cols, vals, false, op->wfwd);
+      } catch (const SpbError& e) {
+        fwd_status = e.status;
+      }
+      if (bwd_thread.joinable()) bwd_thread.join();
+      if (fwd_status != SPB_OK) throw SpbError{fwd_status};
+      if (bwd_status != SPB_OK) throw SpbError{bwd_status};
       if (getenv("SPB_GS_STATS") && op->wfwd.ok) {
         op->wave_stats.alloc(sizeof(long long) * 4 * (size_t)op->wfwd.nblocks);
         SPB_CUDA(cudaMemset(op->wave_stats.p, 0, op->wave_stats.bytes));
       }
+    }
+    // The global level schedule (cooperative grid-barrier kernel) is only the fallback: built now
+    // when a wavefront schedule is unavailable, otherwise on first use (ensure_levels).
+    if (!op->wfwd.ok || (mode == SPB_GS_SYMMETRIC && !op->wbwd.ok)) {
+      build_levels(c, n, ip, cols, true, op->fwd);
+      build_levels(c, n, ip, cols, false, op->bwd);
+      op->levels_ready = true;
     }
   } catch (...) {
     delete op;
     throw;
   }
   return op;
+}
+
+// Fallback schedule on first use (a sweep the wavefront kernel does not take: the produced side is
+// not the output vector).
+template <typename T>
+static void ensure_levels(GsOp<T>* M) {
+  if (M->levels_ready) return;
+  Ctx* c = M->ctx;
+  CsrMat<T>* A = M->A;
+  const int64_t n = A->n_local;
+  std::vector<int64_t> ip(n + 1);
+  std::vector<int> cols((size_t)A->nnz);
+  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  if (A->ip64) {
+    SPB_CUDA(cudaMemcpy(ip.data(), A->indptr.p, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<int> ip32(n + 1);
+    SPB_CUDA(cudaMemcpy(ip32.data(), A->indptr.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i <= n; ++i) ip[i] = ip32[i];
+  }
+  if (A->nnz) SPB_CUDA(cudaMemcpy(cols.data(), A->cols.p, sizeof(int) * A->nnz, cudaMemcpyDeviceToHost));
+  build_levels(c, n, ip, cols, true, M->fwd);
+  build_levels(c, n, ip, cols, false, M->bwd);
+  M->levels_ready = true;
 }
 
 template <typename T, typename IP>
@@ -326,6 +377,7 @@ static void sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, c
     wave_sweep<T>(M, ws, rhs, other, out);
     return;
   }
+  ensure_levels(M);
   if (M->A->ip64)
     launch_sweep<T, int64_t>(M, ls, rhs, lo, hi, out);
   else

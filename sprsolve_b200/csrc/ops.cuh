@@ -46,6 +46,7 @@ struct WaveSched {
   int stages = 0;
   size_t smem_bytes = 0;
   int64_t local_levels_max = 0;
+  int64_t global_levels = 0;  // length of the longest dependency chain (levels of the whole triangle)
   DevBuf stat;       // packed static chunks
   DevBuf chunks;     // WaveChunk [nchunks]
   DevBuf blk_chunk;  // int32 [nblocks+1], blocks in PROCESSING order
@@ -64,7 +65,8 @@ struct GsOp : spb_op {
   CsrMat<T>* A = nullptr;
   int mode = SPB_GS_FORWARD;
   DevBuf diag;          // T [n] cached diagonal (src/gauss_seidel.rs:81)
-  LevelSched fwd, bwd;  // lower / upper pattern (global levels: reported, and the fallback sweep)
+  LevelSched fwd, bwd;  // lower / upper pattern, global levels: the fallback sweep (built on first use)
+  bool levels_ready = false;
   WaveSched wfwd, wbwd; // block-wavefront schedules (the fast path)
   DevBuf tmp;           // T [n]: forward result for the symmetric variant
   DevBuf barrier;       // grid barrier words
