@@ -288,6 +288,39 @@ def test_gauss_seidel_sweep_bit_exact(sp, orc, symmetric):
     assert e.value.row == 0
 
 
+def test_spmv_dictionary_analysis(sp, orc, monkeypatch):
+    """The analysis (MklMat::mv_hint / mkl_sparse_optimize analogue, src/mkl_mat.rs:81-148) finds the
+    column-offset patterns of a stencil matrix; the dictionary kernel is bit-identical to the plain
+    one and to the oracle; matrices it does not pay for keep the plain column stream."""
+    A = orc.gen_convdiff27(14, 13, 12)
+    x = _rand_vec(A.n, np.float64)
+    ref = orc.spmv(A, x)
+    G = to_gpu(sp, A)
+    info = G.plan_info()
+    assert info["dictionary"] == 1 and info["patterns"] == 27  # 3 x 3 x 3 combinations of touched faces
+    assert info["stream_bytes"] == A.nnz * 8 + (A.n + 1) * 4 + 2 * A.n + 16 * A.n
+    y = np.zeros(A.n)
+    G.mul_vec(x, y)
+    assert np.array_equal(y, ref)
+    monkeypatch.setenv("SPB_SPMV_DICT", "0")
+    G0 = to_gpu(sp, A)
+    assert G0.plan_info()["dictionary"] == 0
+    y0 = np.zeros(A.n)
+    G0.mul_vec(x, y0)
+    assert np.array_equal(y0, ref)
+    monkeypatch.delenv("SPB_SPMV_DICT")
+    assert to_gpu(sp, orc.gen_lap3d7(10, 9, 8)).plan_info()["dictionary"] == 0        # 7 entries per row: gather bound
+    assert to_gpu(sp, orc.gen_lap3d7(6, 6, 6, shift=0.5j, dtype=np.complex128)).plan_info()["dictionary"] == 0
+    monkeypatch.setenv("SPB_SPMV_DICT", "1")  # forced: every row its own pattern on a random matrix
+    R = _random_sorted_csr(orc, 500, 0.02, 9)
+    GR = to_gpu(sp, R)
+    assert GR.plan_info()["dictionary"] == 1
+    xr = _rand_vec(R.n, np.float64)
+    yr = np.zeros(R.n)
+    GR.mul_vec(xr, yr)
+    assert np.array_equal(yr, orc.spmv(R, xr))
+
+
 def _random_sorted_csr(orc, n, density, seed, dtype=np.float64):
     """Random pattern (sorted columns, full diagonal, diagonally dominant) -- not a stencil, so rows
     depend on rows far away and on many blocks of the wavefront schedule."""
