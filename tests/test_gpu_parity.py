@@ -321,6 +321,40 @@ def test_spmv_dictionary_analysis(sp, orc, monkeypatch):
     assert np.array_equal(yr, orc.spmv(R, xr))
 
 
+@pytest.mark.parametrize("dict_knob", ["0", "1"])
+def test_edge_shapes(sp, orc, dict_knob, monkeypatch):
+    """Degenerate shapes through every operator: 1x1, purely diagonal (one level, no dependencies),
+    empty rows (src/mat.rs:71 zero fill; KAT row 1 of src/mat.rs:233), a single dense-ish row."""
+    monkeypatch.setenv("SPB_SPMV_DICT", dict_knob)
+    one = orc.Csr(1, np.array([0, 1]), np.array([0], np.int32), np.array([2.5]))
+    diag = orc.Csr(40, np.arange(41), np.arange(40, dtype=np.int32), np.linspace(1.0, 3.0, 40))
+    ip = np.array([0, 2, 2, 5, 5, 5, 6], np.int64)  # rows 1, 3, 4 empty
+    holes = orc.Csr(6, ip, np.array([0, 3, 0, 2, 5, 5], np.int32), np.array([1.0, -2.0, 0.5, 4.0, 1.5, 3.0]))
+    # row 1 touches every column
+    wide = orc.Csr(50, np.concatenate([[0, 1], [51], np.arange(52, 100)]).astype(np.int64)[:51],
+                   np.concatenate([[0], np.arange(0, 50), np.arange(2, 50)]).astype(np.int32),
+                   np.concatenate([[2.0], np.full(50, 0.01), np.full(48, 3.0)]))
+    wide.data[1 + 1] = 5.0  # diagonal of row 1
+    for A in (one, diag, holes, wide):
+        x = _rand_vec(A.n, np.float64)
+        G = to_gpu(sp, A)
+        y = np.full(A.n, 7.0)
+        G.mul_vec(x, y)
+        assert np.array_equal(y, orc.spmv(A, x))
+        y2 = np.zeros(A.n)
+        d = G.mul_vec_dot(x, y2)
+        assert np.array_equal(y2, y) and abs(d - np.dot(x, y)) <= 1e-13 * max(1.0, abs(np.dot(x, y)))
+    for A in (one, diag, wide):  # full diagonal: Gauss-Seidel is defined
+        G = to_gpu(sp, A)
+        v = _rand_vec(A.n, np.float64)
+        for symmetric in (False, True):
+            out = np.zeros(A.n)
+            sp.GaussSeidelPrecond(G, symmetric=symmetric).mul_vec(v, out)
+            assert np.array_equal(out, orc.gs_apply(A, v, symmetric))
+    with pytest.raises(sp.ZeorDiagonalElem):
+        sp.GaussSeidelPrecond(to_gpu(sp, holes))
+
+
 def _random_sorted_csr(orc, n, density, seed, dtype=np.float64):
     """Random pattern (sorted columns, full diagonal, diagonally dominant) -- not a stencil, so rows
     depend on rows far away and on many blocks of the wavefront schedule."""
