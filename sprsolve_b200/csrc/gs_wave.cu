@@ -38,6 +38,8 @@
 //   * one thread per row folds sigma sequentially in CSR order (src/gauss_seidel.rs:113-118) with
 //     separate multiply and add (-fmad=false): every x_i is bit-identical to the reference loop.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -382,6 +384,14 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   const int64_t n = A->n_local;
   ws.ok = false;
   ws.backward = backward;
+  const bool timing = getenv("SPB_GS_TIMING") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[gs_wave %s] %-12s %.1f ms\n", backward ? "bwd" : "fwd", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   if (n <= 0 || n >= ((int64_t)1 << 31) - 1 || getenv("SPB_GS_LEGACY")) return;
   auto env = [](const char* name, int dflt) {
     const char* e = getenv(name);
@@ -456,6 +466,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
     ws.global_levels = (int64_t)gl + 1;
   }
 
+  lap("levels");
   // per-row counts: produced entries, other-side entries, produced entries outside the block;
   // ext_out[j]: how many rows of OTHER blocks read x_j (an upper bound of the mailbox slots row j
   // delivers to -- slots are shared by the rows of one consumer chunk)
@@ -490,6 +501,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
     rinfo[i] = ri;
   }
 
+  lap("row info");
   // ---- pass A: chunk membership, mailbox ranges ------------------------------------------------
   struct Plan {
     int row_beg, row_end;  // into plan_rows
@@ -597,6 +609,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   }
   if (mb_total >= ((long long)1 << 32) - 16) return;  // mailbox slots are addressed with 32 bits
 
+  lap("pass A");
   // ---- mail lists: which slots want the value of row j ----------------------------------------
   std::vector<int64_t> mail_ptr(n + 1, 0);
   for (const Plan& pl : plans)
@@ -609,6 +622,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
       for (int q = pl.hal_beg; q < pl.hal_end; ++q) mail_idx[(size_t)cur[plan_halo[q]]++] = (uint32_t)(pl.mb_off + (q - pl.hal_beg));
   }
 
+  lap("mail lists");
   // ---- pass B: emit the packed chunks ----------------------------------------------------------
   std::vector<int> slot_of(n, -1);  // column -> slot inside the chunk being emitted
   for (size_t ci = 0; ci < plans.size(); ++ci) {
@@ -696,6 +710,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
     put_bytes(stat, base + L.hslot, hs.data(), hs.size());
     chunks.push_back(d);
   }
+  lap("pass B");
   blk_chunk[nb] = (int)chunks.size();
   ws.nchunks = (int64_t)chunks.size();
   ws.rhs_slots = (int64_t)rowmap.size();
@@ -725,6 +740,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   SPB_CUDA(cudaMemsetAsync(ws.rhsp.p, 0, ws.rhsp.bytes, c->stream));
   SPB_CUDA(cudaMemsetAsync(ws.aux.p, 0, ws.aux.bytes, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));  // the host vectors go out of scope
+  lap("upload");
   ws.ok = true;
 }
 
