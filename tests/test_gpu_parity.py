@@ -676,3 +676,74 @@ def test_spmv_config2_full_size_properties(sp):
     assert float(g[0, 0, 0]) == 3.0 and float(g[0, 5, 5]) == 1.0
     assert torch.allclose(yc, 0.75 * yx - 1.25 * yz, rtol=0, atol=1e-12)
     assert abs(float(yx.sum()) - float((ya * x).sum())) <= 1e-9 * float(yx.abs().sum())
+
+
+def test_spmv_config5_full_size_dictionary_equals_plain(sp, monkeypatch):
+    """Config C5 at full size (512^3 27-point, 3.6 G non-zeros, int64 row pointers): the dictionary
+    kernel and the plain CSR kernel give the same bits, interior rows of A*1 sum to exactly zero
+    (27.75 - 26 - 1 - 0.5 - 0.25), and the fused <w, y> epilogue agrees with a separate dot."""
+    import torch
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~60 GB of device memory")
+    n1 = 512
+    n = n1**3
+    dev = torch.device("cuda:0")
+    k = torch.arange(n, device=dev)
+    x = torch.cos(k.double() * 1e-3) + 0.25
+    ones = torch.ones(n, dtype=torch.float64, device=dev)
+    del k
+    ys = []
+    for knob in ("1", "0"):
+        monkeypatch.setenv("SPB_SPMV_DICT", knob)
+        G = sp.GpuCsrMat.from_stencil(sp.STENCIL_CONVDIFF27, n1, n1, n1, params=(1.0, 0.5, 0.25))
+        assert G.nnz == (3 * n1 - 2) ** 3 == 3609741304
+        info = G.plan_info()
+        assert info["dictionary"] == int(knob) and (knob == "0" or info["patterns"] == 27)
+        y = torch.empty(n, dtype=torch.float64, device=dev)
+        G.mul_vec_dev(x.data_ptr(), y.data_ptr())
+        if knob == "1":
+            ya = torch.empty(n, dtype=torch.float64, device=dev)
+            G.mul_vec_dev(ones.data_ptr(), ya.data_ptr())
+            G.ctx.synchronize()
+            assert float(ya.view(n1, n1, n1)[1:-1, 1:-1, 1:-1].abs().max()) == 0.0
+            d = G.mul_vec_dot_dev(x.data_ptr(), ya.data_ptr())  # ya := A x, d = <x, A x>
+            G.ctx.synchronize()
+            assert torch.equal(ya, y)
+            ref = float(torch.dot(x, y))
+            assert abs(d - ref) <= 1e-12 * abs(ref)
+            del ya
+        G.ctx.synchronize()
+        ys.append(y)
+        G.destroy()
+        torch.cuda.empty_cache()
+    assert torch.equal(ys[0], ys[1])
+
+
+def test_gauss_seidel_config3_full_size_wavefront_equals_level_schedule(sp, monkeypatch):
+    """Config C3 at full size (128^3 shifted 7-point): the block-wavefront sweep and the global level
+    schedule with grid barriers (two independent kernels and analyses) produce the same bits for the
+    symmetric Gauss-Seidel apply; 382 levels each way (hyperplanes i+j+k)."""
+    import torch
+
+    g = 128
+    n = g**3
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    r = torch.rand(n, dtype=torch.float64, device=dev) - 0.5
+    outs = []
+    for legacy in (False, True):
+        if legacy:
+            monkeypatch.setenv("SPB_GS_LEGACY", "1")
+        A = sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, g, g, g, params=(0.05,))
+        M = sp.GaussSeidelPrecond(A, symmetric=True)
+        assert M.levels() == (3 * (g - 1) + 1, 3 * (g - 1) + 1)
+        assert M.schedule_info()["fwd_ok"] == (0 if legacy else 1)
+        z = torch.empty_like(r)
+        M.mul_vec_dev(r.data_ptr(), z.data_ptr())
+        M.mul_vec_dev(r.data_ptr(), z.data_ptr())  # schedules are re-usable
+        A.ctx.synchronize()
+        outs.append(z)
+    assert torch.equal(outs[0], outs[1])
+    assert M.schedule_info()["poll_timeout"] == 0
