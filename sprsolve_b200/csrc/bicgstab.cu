@@ -119,18 +119,18 @@ __global__ void bicg_s3(BicgState<T>* st, const scal2* red) {
 // ---------------------------------------------------------------- vector kernels
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads)
-bicg_k_init(const BicgState<T>* st, int restart, int64_t n, const T* rhs, T* r, T* r0, T* partials) {
-  T e0 = zero_of<T>();
+bicg_k_init(const BicgState<T>* st, int restart, int64_t n, const T* rhs, T* r, T* r0, Acc<T>* partials) {
+  Acc<T> e0 = zero_of<Acc<T>>();
   if (restart ? st->h.status == DS_NEED_RESTART : st->h.status == DS_RUNNING) {
     const T m1 = neg(one_of<T>());
     SPB_GRID_STRIDE(i, n) {
       const T ri = add(r[i], mul(rhs[i], m1));  // axpy(-1, rhs, r), :246
       r[i] = ri;
       r0[i] = ri;                               // :249
-      e0 = add(e0, from_real<T>(square(ri)));   // norm2, :251
+      acc_sq(e0, ri);                           // norm2, :251
     }
   }
-  write_partials(e0, zero_of<T>(), partials);
+  write_partials(e0, zero_of<Acc<T>>(), partials);
 }
 
 template <typename T, typename V, bool FIRST, bool WRITE_Y>
@@ -166,8 +166,8 @@ bicg_k2(const BicgState<T>* st, int64_t n, T* r, const T* v, T* z, const V* dinv
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads)
 bicg_k3(const BicgState<T>* st, int64_t n, T* x, const T* y, const T* z, T* r, const T* t, const T* r0,
-        T* partials) {
-  T e0 = zero_of<T>(), e1 = zero_of<T>();
+        Acc<T>* partials) {
+  Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
   if (st->h.status == DS_RUNNING) {
     const T nalpha = st->nalpha, nw = st->nw;
     SPB_GRID_STRIDE(i, n) {
@@ -177,8 +177,8 @@ bicg_k3(const BicgState<T>* st, int64_t n, T* x, const T* y, const T* z, T* r, c
       x[i] = xi;
       const T ri = add(r[i], mul(t[i], nw));  // axpy(-w, t, r), :362
       r[i] = ri;
-      e0 = add(e0, from_real<T>(square(ri)));      // next norm2(r), :296
-      e1 = add(e1, mul(conj_of(r0[i]), ri));       // next conj_dot(r0, r), :301
+      acc_sq(e0, ri);                    // next norm2(r), :296
+      acc_prod(e1, conj_of(r0[i]), ri);  // next conj_dot(r0, r), :301
     }
   }
   write_partials(e0, e1, partials);
@@ -188,7 +188,7 @@ bicg_k3(const BicgState<T>* st, int64_t n, T* x, const T* y, const T* z, T* r, c
 template <typename T>
 struct BicgStab : spb_solver {
   DevBuf ws;        // 7 n T  (src/bicg_stab.rs:28)
-  DevBuf partials;  // T [2 * max grid]
+  DevBuf partials;  // Acc<T> [2 * max grid]
   DevBuf red;       // scal2 [2]
   DevBuf state;     // BicgState<T>
   DevBuf hist_d;
@@ -201,7 +201,7 @@ struct BicgStab : spb_solver {
     size = size_;
     ws.alloc(sizeof(T) * 7 * (size_t)std::max<int64_t>(size, 1));
     SPB_CUDA(cudaMemsetAsync(ws.p, 0, ws.bytes, ctx->stream));
-    partials.alloc(sizeof(T) * 2 * (size_t)(vec_max_grid(ctx) + 1));
+    partials.alloc(sizeof(Acc<T>) * 2 * (size_t)(vec_max_grid(ctx) + 1));
     red.alloc(sizeof(scal2) * 2);
     state.alloc(sizeof(BicgState<T>));
   }
@@ -235,7 +235,7 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   const void* dinv = (pcm == PCM_JACOBI || pcm == PCM_JACOBI_REAL) ? static_cast<DiagOp<T>*>(M)->dinv.p : nullptr;
   auto* st = bufptr<BicgState<T>>(state);
   scal2* redp = bufptr<scal2>(red);
-  T* parts = bufptr<T>(partials);
+  Acc<T>* parts = bufptr<Acc<T>>(partials);
   const int grid = vec_grid(c, n);
   const long long cap = hist ? std::min<int64_t>(hist_cap, max_iter + 1) : 0;
   double* hd = nullptr;
@@ -316,8 +316,7 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   c->gate = nullptr;
   try {
     // ||b||                                                           (:225-231)
-    vec_reduce<T>(c, 2, n, rhs, rhs, parts, redp);
-    allreduce_sum(c, (double*)redp, 4);
+    vec_reduce<T>(c, 2, n, rhs, rhs, parts, redp, true);
     scalar(bicg_s_rhs<T>, st, redp);
     poller.post(st);
     poller.drain(&hd_host);

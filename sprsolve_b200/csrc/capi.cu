@@ -663,9 +663,9 @@ template <typename T>
 void vec_reduce_host(Ctx* c, int kind, int64_t n, const void* x, const void* y, double out[2]) {
   HostVec<T> dx(c, x, n), dy(c, y ? y : x, n);
   DevBuf parts, red;
-  parts.alloc(sizeof(T) * 2 * (size_t)(vec_max_grid(c) + 1));
+  parts.alloc(sizeof(Acc<T>) * 2 * (size_t)(vec_max_grid(c) + 1));
   red.alloc(sizeof(scal2) * 2);
-  vec_reduce<T>(c, kind, n, dx.p(), dy.p(), bufptr<T>(parts), bufptr<scal2>(red));
+  vec_reduce<T>(c, kind, n, dx.p(), dy.p(), bufptr<Acc<T>>(parts), bufptr<scal2>(red));
   scal2 h[2];
   SPB_CUDA(cudaMemcpyAsync(h, red.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));

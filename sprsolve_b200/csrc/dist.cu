@@ -56,9 +56,12 @@ int Ctx::world() const { return dist ? dist->world : 1; }
 int Ctx::rank() const { return dist ? dist->rank : 0; }
 
 __global__ void peer_allreduce_kernel(double* v, int count, PeerPtrs pp) {
-  __shared__ double loc[4];
-  if (threadIdx.x < 4) loc[threadIdx.x] = (int)threadIdx.x < count ? v[threadIdx.x] : 0.0;
-  peer_allreduce4(loc, pp);
+  __shared__ double loc[8];
+  if (threadIdx.x < 4) {  // plain doubles: (hi, lo) = (v, 0)
+    loc[2 * threadIdx.x] = (int)threadIdx.x < count ? v[threadIdx.x] : 0.0;
+    loc[2 * threadIdx.x + 1] = 0.0;
+  }
+  peer_allreduce_dd(loc, pp);
   if ((int)threadIdx.x < count) v[threadIdx.x] = loc[threadIdx.x];
 }
 

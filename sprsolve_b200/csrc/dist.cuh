@@ -63,6 +63,7 @@ struct Dist {
   ncclComm_t comm = nullptr;       // scalar all-reduces (NCCL transport), set-up all-gathers
   ncclComm_t comm_halo = nullptr;  // halo send/recv (NCCL transport), on the comm stream
   DevBuf scratch;                  // small device scratch for all-gathers
+  DevBuf dd_buf;                   // NCCL transport: unrounded (hi, lo) pairs of a reduction point, [1 + world][8]
   // peer-memory transport (default; SPB_COMM=nccl selects the NCCL transport instead)
   bool peer = false;
   PeerWindow* scal = nullptr;      // ScalWin of every rank

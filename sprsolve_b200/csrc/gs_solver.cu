@@ -31,17 +31,17 @@ __global__ void gs_s_check(GsState* st, const scal2* red, long long it, double* 
 
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads)
-gs_k_resid(const GsState* st, int64_t n, const T* rhs, T* res, T* partials) {
-  T e0 = zero_of<T>();
+gs_k_resid(const GsState* st, int64_t n, const T* rhs, T* res, Acc<T>* partials) {
+  Acc<T> e0 = zero_of<Acc<T>>();
   if (st->h.status == DS_RUNNING) {
     const T m1 = neg(one_of<T>());
     SPB_GRID_STRIDE(i, n) {
       const T ri = add(res[i], mul(rhs[i], m1));  // axpy(-1, rhs, r), :97 / :131
       res[i] = ri;
-      e0 = add(e0, from_real<T>(square(ri)));     // norm2, :104 / :133
+      acc_sq(e0, ri);                             // norm2, :104 / :133
     }
   }
-  write_partials(e0, zero_of<T>(), partials);
+  write_partials(e0, zero_of<Acc<T>>(), partials);
 }
 
 template <typename T>
@@ -58,7 +58,7 @@ struct GaussSeidelSolver : spb_solver {
     const size_t n1 = (size_t)std::max<int64_t>(size, 1);
     res.alloc(sizeof(T) * n1);   // workspace[0..n]   (src/gauss_seidel.rs:29)
     xalt.alloc(sizeof(T) * n1);
-    partials.alloc(sizeof(T) * 2 * (size_t)(vec_max_grid(ctx) + 1));
+    partials.alloc(sizeof(Acc<T>) * 2 * (size_t)(vec_max_grid(ctx) + 1));
     red.alloc(sizeof(scal2) * 2);
     state.alloc(sizeof(GsState));
   }
@@ -88,7 +88,7 @@ int GaussSeidelSolver<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int
   T* xbuf[2] = {(T*)d_x, bufptr<T>(xalt)};
   auto* st = bufptr<GsState>(state);
   scal2* redp = bufptr<scal2>(red);
-  T* parts = bufptr<T>(partials);
+  Acc<T>* parts = bufptr<Acc<T>>(partials);
   T* resv = bufptr<T>(res);
   const int grid = vec_grid(c, n);
   const long long cap = hist ? std::min<int64_t>(hist_cap, max_iter) : 0;

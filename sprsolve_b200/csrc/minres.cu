@@ -129,18 +129,18 @@ __global__ void mr_s_givens(MinresState<T>* st, const scal2* red, const scal2* b
 template <typename T, typename V, bool JACOBI>
 __global__ void __launch_bounds__(kVecThreads)
 mr_k_init(const MinresState<T>* st, int64_t n, const T* rhs, const T* v_old, T* v_new, T* v, T* p_old, T* p,
-          T* w_new, const V* dinv, T* partials) {
-  T e0 = zero_of<T>(), e1 = zero_of<T>();
+          T* w_new, const V* dinv, Acc<T>* partials) {
+  Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
   if (st->h.status == DS_RUNNING) {
     const T m1 = neg(one_of<T>()), z = zero_of<T>();
     SPB_GRID_STRIDE(i, n) {
       const T vn = add(rhs[i], mul(v_old[i], m1));  // axpy(-1, v_old, v_new), :80
       v_new[i] = vn;
-      e0 = add(e0, from_real<T>(square(vn)));       // :81
+      acc_sq(e0, vn);                               // :81
       if (JACOBI) {
         const T wn = mul_diag(vn, dinv[i]);         // w_new = M v_new, :233
         w_new[i] = wn;
-        e1 = add(e1, mul(conj_of(vn), wn));         // :235
+        acc_prod(e1, conj_of(vn), wn);              // :235
       }
       v[i] = z;
       p_old[i] = z;
@@ -164,19 +164,19 @@ mr_k_scale(const MinresState<T>* st, int64_t n, T* v_new, T* w_new) {
 template <typename T, typename V, bool JACOBI>
 __global__ void __launch_bounds__(kVecThreads)
 mr_k1(const MinresState<T>* st, int64_t n, T* v_new, const T* v_old, const T* v, T* w_new, const V* dinv,
-      T* partials) {
-  T e0 = zero_of<T>(), e1 = zero_of<T>();
+      Acc<T>* partials) {
+  Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
   if (st->h.status == DS_RUNNING) {
     const T nbeta = st->nbeta, nalpha = st->nalpha;
     SPB_GRID_STRIDE(i, n) {
       T vn = add(v_new[i], mul(v_old[i], nbeta));  // :117
       vn = add(vn, mul(v[i], nalpha));             // :118
       v_new[i] = vn;
-      e0 = add(e0, from_real<T>(square(vn)));      // :120
+      acc_sq(e0, vn);                              // :120
       if (JACOBI) {
         const T wn = mul_diag(vn, dinv[i]);        // :276
         w_new[i] = wn;
-        e1 = add(e1, mul(conj_of(vn), wn));        // :278
+        acc_prod(e1, conj_of(vn), wn);             // :278
       }
     }
   }
@@ -216,7 +216,7 @@ struct MinRes : spb_solver {
     size = size_;
     ws.alloc(sizeof(T) * (cs ? 7 : 8) * (size_t)std::max<int64_t>(size, 1));
     SPB_CUDA(cudaMemsetAsync(ws.p, 0, ws.bytes, ctx->stream));  // vec![T::zero(); size*8]
-    partials.alloc(sizeof(T) * 2 * (size_t)(vec_max_grid(ctx) + 1));
+    partials.alloc(sizeof(Acc<T>) * 2 * (size_t)(vec_max_grid(ctx) + 1));
     red.alloc(sizeof(scal2) * 2);
     red2.alloc(sizeof(scal2) * 2);
     state.alloc(sizeof(MinresState<T>));
@@ -251,7 +251,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
   auto* st = bufptr<MinresState<T>>(state);
   scal2* redp = bufptr<scal2>(red);
   scal2* red2p = bufptr<scal2>(red2);
-  T* parts = bufptr<T>(partials);
+  Acc<T>* parts = bufptr<Acc<T>>(partials);
   const int grid = vec_grid(c, n);
   const long long cap = hist ? std::min<int64_t>(hist_cap, max_iter) : 0;
   double* hd = nullptr;
@@ -276,8 +276,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
   // b2 = <v_new, w_new> for a generic preconditioner (separate apply + conj_dot)
   auto generic_b2 = [&](T* vn, T* wn) {
     op_apply<T>(M, vn, wn);
-    vec_reduce<T>(c, 1, n, vn, wn, parts, red2p);  // gated apply; the dot itself is harmless
-    allreduce_sum(c, (double*)red2p, 4);
+    vec_reduce<T>(c, 1, n, vn, wn, parts, red2p, true);  // gated apply; the dot itself is harmless
   };
   const scal2* b2src = jac ? redp + 1 : red2p;
 
@@ -286,8 +285,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
   StateHead hh;
   c->gate = nullptr;
   try {
-    vec_reduce<T>(c, 2, n, rhs, rhs, parts, redp);
-    allreduce_sum(c, (double*)redp, 4);
+    vec_reduce<T>(c, 2, n, rhs, rhs, parts, redp, true);
     scalar(mr_s_rhs<T>, st, redp);
     poller.post(st);
     poller.drain(&hh);

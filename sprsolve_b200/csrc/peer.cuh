@@ -27,7 +27,7 @@ struct PeerPtrs {
 
 // Scalar all-reduce window (one per context).
 struct ScalWin {
-  double slots[2][kMaxPeers][4];
+  double slots[2][kMaxPeers][8];  // one reduction point: 4 (hi, lo) pairs -- slot 0 (re, im), slot 1 (re, im)
   unsigned long long flags[2][kMaxPeers];
   unsigned long long seq;
   int error;  // set when a spin timed out (a peer died): surfaces as SPB_NCCL_ERROR on the host
@@ -72,9 +72,11 @@ __device__ __forceinline__ bool spin_until_ge(const unsigned long long* flag, un
   }
 }
 
-// Sum loc[0..3] over all ranks; called by ONE CTA with >= kMaxPeers threads, all threads.
-// loc lives in shared memory; on return loc holds the global sums (identical bits on every rank).
-__device__ __forceinline__ void peer_allreduce4(double* loc, const PeerPtrs& pp) {
+// Sum a reduction point over all ranks; called by ONE CTA with >= kMaxPeers threads, all threads.
+// loc (shared memory) holds this rank's 4 double-double pairs (hi, lo) x {slot 0 re, im, slot 1 re,
+// im}; on return loc[0..3] hold the four sums ROUNDED to double (identical bits on every rank, and
+// -- because the pairs carry the sums exactly -- identical for every partition of the rows).
+__device__ __forceinline__ void peer_allreduce_dd(double* loc, const PeerPtrs& pp) {
   ScalWin* me = static_cast<ScalWin*>(pp.p[pp.rank]);
   const unsigned long long seq = *((volatile unsigned long long*)&me->seq) + 1;
   const int par = (int)(seq & 1);
@@ -83,30 +85,29 @@ __device__ __forceinline__ void peer_allreduce4(double* loc, const PeerPtrs& pp)
   if (t < pp.world) {
     ScalWin* dst = static_cast<ScalWin*>(pp.p[t]);
     volatile double* s = dst->slots[par][pp.rank];
-    s[0] = loc[0];
-    s[1] = loc[1];
-    s[2] = loc[2];
-    s[3] = loc[3];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = loc[k];
     __threadfence_system();
     st_release_sys(&dst->flags[par][pp.rank], seq);
     if (!spin_until_ge(&me->flags[par][t], seq)) me->error = 1;
   }
   __syncthreads();
-  if (t == 0) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    for (int q = 0; q < pp.world; ++q) {  // rank order: the same sum on every rank
+  if (t < 4) {  // pair t: double-double sum over the ranks in rank order, then ONE rounding
+    double hi = 0.0, lo = 0.0;
+    for (int q = 0; q < pp.world; ++q) {
       const volatile double* s = me->slots[par][q];
-      a0 += s[0];
-      a1 += s[1];
-      a2 += s[2];
-      a3 += s[3];
+      const double h = s[2 * t], l = s[2 * t + 1];
+      lo += l;
+      const double sum = hi + h;
+      const double bb = sum - hi;
+      lo += (hi - (sum - bb)) + (h - bb);
+      hi = sum;
     }
-    loc[0] = a0;
-    loc[1] = a1;
-    loc[2] = a2;
-    loc[3] = a3;
-    *((volatile unsigned long long*)&me->seq) = seq;
+    __syncwarp(0xfu);
+    loc[t] = hi + lo;
   }
+  __syncthreads();
+  if (t == 0) *((volatile unsigned long long*)&me->seq) = seq;
   __syncthreads();
 }
 #endif  // __CUDACC__

@@ -1,10 +1,19 @@
-// reduce.cuh -- deterministic block reductions (no float atomics anywhere in the library).
+// reduce.cuh -- deterministic, order-independent block reductions (no float atomics anywhere).
 //
 // Every long sum of the reference (vecalg::conj_dot / norm2, src/vecalg.rs:563-568,601-605) is a
 // sequential left fold.  On the GPU a sum is split into per-thread partial folds, a fixed shuffle
 // tree per warp, a fixed-order fold over warps, one partial per block written to memory and a
-// final fixed-order pass over the block partials.  Grid sizes depend only on the problem, so the
-// result is bit-reproducible run to run; it differs from the reference only by summation order.
+// final fixed-order pass over the block partials (and, when partitioned, over the ranks).
+//
+// A plain double sum would make the RESULT depend on that split: on the launch plan of the SpMV
+// (fused epilogue dots), on the grid size and on the number of GPUs -- and Jacobi-BiCGStab turns a
+// 1e-16 difference of one dot product into a different iteration count (615..668 iterations on the
+// 512^3 system, measured).  So the sums are carried in double-double (Acc<T>): every product is
+// split exactly (p = a*b rounded, e = fma(a, b, -p)), partial sums are combined with error-free
+// two-sums, and only the final value is rounded to double.  The rounded result is the correctly
+// rounded exact sum except in astronomically rare near-tie cases, hence the same bits for every
+// plan, grid and GPU count; it differs from the reference's sequential fold by that fold's own
+// rounding error (1e-16 * sqrt(n) relative), i.e. exactly as a re-ordered sum would.
 #pragma once
 #include "scalar.cuh"
 
@@ -15,6 +24,83 @@ __device__ __forceinline__ double shfl_down(double v, int d) {
 }
 __device__ __forceinline__ cplx shfl_down(cplx v, int d) {
   return cplx{__shfl_down_sync(0xffffffffu, v.re, d), __shfl_down_sync(0xffffffffu, v.im, d)};
+}
+
+// ---- double-double accumulators -----------------------------------------------------------------
+template <typename T>
+struct Acc;
+template <>
+struct __align__(16) Acc<double> {
+  double hi, lo;
+};
+template <>
+struct __align__(16) Acc<cplx> {
+  double rh, rl, ih, il;
+};
+template <>
+SPB_HD Acc<double> zero_of<Acc<double>>() {
+  return Acc<double>{0.0, 0.0};
+}
+template <>
+SPB_HD Acc<cplx> zero_of<Acc<cplx>>() {
+  return Acc<cplx>{0.0, 0.0, 0.0, 0.0};
+}
+// (hi, lo) += x, x an exact double: error-free two-sum on hi, the error goes to lo
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double x) {
+  const double s = hi + x;
+  const double bb = s - hi;
+  lo += (hi - (s - bb)) + (x - bb);
+  hi = s;
+}
+// (hi, lo) += a * b exactly (the product error comes from one fma)
+__device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double a, double b) {
+  const double p = a * b;
+  lo += __fma_rn(a, b, -p);
+  dd_add(hi, lo, p);
+}
+__device__ __forceinline__ void acc_prod(Acc<double>& a, double x, double y) { dd_add_prod(a.hi, a.lo, x, y); }
+__device__ __forceinline__ void acc_prod(Acc<cplx>& a, cplx x, cplx y) {  // a += x * y
+  dd_add_prod(a.rh, a.rl, x.re, y.re);
+  dd_add_prod(a.rh, a.rl, -x.im, y.im);
+  dd_add_prod(a.ih, a.il, x.re, y.im);
+  dd_add_prod(a.ih, a.il, x.im, y.re);
+}
+__device__ __forceinline__ void acc_sq(Acc<double>& a, double x) { dd_add_prod(a.hi, a.lo, x, x); }  // a += |x|^2
+__device__ __forceinline__ void acc_sq(Acc<cplx>& a, cplx x) {
+  dd_add_prod(a.rh, a.rl, x.re, x.re);
+  dd_add_prod(a.rh, a.rl, x.im, x.im);
+}
+__device__ __forceinline__ Acc<double> add(Acc<double> a, Acc<double> b) {
+  a.lo += b.lo;
+  dd_add(a.hi, a.lo, b.hi);
+  return a;
+}
+__device__ __forceinline__ Acc<cplx> add(Acc<cplx> a, Acc<cplx> b) {
+  a.rl += b.rl;
+  dd_add(a.rh, a.rl, b.rh);
+  a.il += b.il;
+  dd_add(a.ih, a.il, b.ih);
+  return a;
+}
+__device__ __forceinline__ Acc<double> shfl_down(Acc<double> v, int d) {
+  return Acc<double>{__shfl_down_sync(0xffffffffu, v.hi, d), __shfl_down_sync(0xffffffffu, v.lo, d)};
+}
+__device__ __forceinline__ Acc<cplx> shfl_down(Acc<cplx> v, int d) {
+  return Acc<cplx>{__shfl_down_sync(0xffffffffu, v.rh, d), __shfl_down_sync(0xffffffffu, v.rl, d),
+                   __shfl_down_sync(0xffffffffu, v.ih, d), __shfl_down_sync(0xffffffffu, v.il, d)};
+}
+// the four (hi, lo) pairs a reduction point carries: slot 0 (re, im), slot 1 (re, im)
+__device__ __forceinline__ void acc_store(const Acc<double>& a, double* dd4) {
+  dd4[0] = a.hi;
+  dd4[1] = a.lo;
+  dd4[2] = 0.0;
+  dd4[3] = 0.0;
+}
+__device__ __forceinline__ void acc_store(const Acc<cplx>& a, double* dd4) {
+  dd4[0] = a.rh;
+  dd4[1] = a.rl;
+  dd4[2] = a.ih;
+  dd4[3] = a.il;
 }
 
 template <typename T>

@@ -27,6 +27,7 @@
 #include "reduce.cuh"
 
 #include "tma.cuh"
+#include "vecops.cuh"
 
 namespace spb {
 
@@ -59,7 +60,7 @@ struct SpmvArgs {
   int n_local;
   T* y;
   const T* w;    // epilogue operand
-  T* partials;   // [2 * gridDim.x]
+  Acc<T>* partials;  // [2 * gridDim.x] double-double partial sums of the epilogue
   const int* gate;  // optional solver gate (see Ctx::gate)
   int gate_value;
   int tile;      // staging capacity in non-zeros (multiple of 4)
@@ -90,13 +91,13 @@ __device__ __forceinline__ T gather_x(const T* x, const T* xh_adj, int n_local, 
 }
 
 template <typename T, int EPI>
-__device__ __forceinline__ void epilogue_acc(T acc, const T* w, int64_t r, T& e0, T& e1) {
+__device__ __forceinline__ void epilogue_acc(T acc, const T* w, int64_t r, Acc<T>& e0, Acc<T>& e1) {
   if (EPI == EPI_DOT_WY) {
-    e0 = add(e0, mul(conj_of(w[r]), acc));  // conj_dot(w, y): src/vecalg.rs:564-568
+    acc_prod(e0, conj_of(w[r]), acc);  // conj_dot(w, y): src/vecalg.rs:564-568
   } else if (EPI == EPI_TT_TR) {
     const T cy = conj_of(acc);
-    e0 = add(e0, mul(cy, acc));   // conj_dot(t, t)
-    e1 = add(e1, mul(cy, w[r]));  // conj_dot(t, r)
+    acc_prod(e0, cy, acc);   // conj_dot(t, t)
+    acc_prod(e1, cy, w[r]);  // conj_dot(t, r)
   }
 }
 
@@ -152,7 +153,8 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
   uint64_t* empty = full + kMaxStages;
   TileMeta* meta = reinterpret_cast<TileMeta*>(empty + kMaxStages);
-  T* s_red = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(meta + kMaxStages) + 15) & ~(uintptr_t)15);
+  Acc<T>* s_acc = reinterpret_cast<Acc<T>*>((reinterpret_cast<uintptr_t>(meta + kMaxStages) + 15) & ~(uintptr_t)15);
+  T* s_red = reinterpret_cast<T*>(s_acc);  // (scratch of the long-row path; never live at the same time)
 
   if (a.gate && *a.gate != a.gate_value) return;
   const int tid = threadIdx.x;
@@ -168,7 +170,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   const int64_t my_tiles = a.ntiles > (int64_t)blockIdx.x
                                ? (a.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x
                                : 0;
-  T e0 = zero_of<T>(), e1 = zero_of<T>();
+  Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
   const T* xh = a.xh;
   unsigned long long hseq = 0;
   if (HALO && a.hhead) {  // the put kernel queued before this launch has set seq for this exchange
@@ -335,8 +337,8 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
     }
   }
   if (EPI != EPI_NONE) {
-    e0 = block_sum(e0, s_red);
-    if (EPI == EPI_TT_TR) e1 = block_sum(e1, s_red);
+    e0 = block_sum(e0, s_acc);
+    if (EPI == EPI_TT_TR) e1 = block_sum(e1, s_acc);
     if (tid == 0) {
       a.partials[2 * blockIdx.x] = e0;
       a.partials[2 * blockIdx.x + 1] = e1;
@@ -380,25 +382,6 @@ __global__ void max_row_kernel(const IP* indptr, int64_t n, unsigned long long* 
     m = o > m ? o : m;
   }
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);  // integer atomic: order-independent
-}
-
-// Fixed-order sum of the per-CTA epilogue partials; PEER: the sum over ranks is done in the same
-// CTA through the peers' scalar windows (peer.cuh) -- no separate collective launch.
-template <typename T, bool PEER>
-__global__ void finalize_partials_kernel(const T* partials, int64_t nblocks, scal2* red, PeerPtrs pp) {
-  __shared__ T scratch[32];
-  __shared__ double loc[4];
-  for (int slot = 0; slot < 2; ++slot) {
-    const T s = block_sum_partials(partials + slot, nblocks, 2, scratch);
-    if (threadIdx.x == 0) {
-      const scal2 v = to_scal2(s);
-      loc[2 * slot] = v.re;
-      loc[2 * slot + 1] = v.im;
-    }
-  }
-  if (PEER) peer_allreduce4(loc, pp);
-  else __syncthreads();
-  if (threadIdx.x < 2) red[threadIdx.x] = scal2{loc[2 * threadIdx.x], loc[2 * threadIdx.x + 1]};
 }
 
 // ---------------------------------------------------------------- column-offset dictionary
@@ -539,7 +522,7 @@ template <typename T, typename IP>
 static size_t spmv_smem_bytes(const CsrMat<T>* m) {
   const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + (m->dict_on ? 0 : align16i((m->plan_tile + 4) * 4)) +
                        align16i((m->plan_rcap + 8) * (int)sizeof(IP));
-  return m->plan_stages * stage + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(T) + 32;
+  return m->plan_stages * stage + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(Acc<T>) + 32;
 }
 
 // Runs f(kernel_pointer) for the kernel instance selected by (halo, epi, conj).
@@ -637,7 +620,7 @@ void CsrMat<T>::analyze() {
   int stages = env_int("SPB_SPMV_STAGES", 0);
   if (stages <= 0) stages = mean <= 12.0 ? 2 : 1;  // (also the best choice for the dictionary kernel: profiles/r01_spmv_dict.txt)
   build_plan(ct, stages);
-  partials.alloc(sizeof(T) * 2 * (size_t)(2 * (int64_t)c->sm_count * 32 + 2));
+  partials.alloc(sizeof(Acc<T>) * 2 * (size_t)(2 * (int64_t)c->sm_count * 32 + 2));
   red.alloc(sizeof(scal2) * 2);
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->dist && !peers.empty()) classify_tiles(this);
@@ -746,14 +729,14 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
     if (ip64) {
       SpmvArgs<T, int64_t> a{bufptr<int64_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, halo_ptr, (int)n_local, y, w,
-                             bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
+                             bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
                              bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w};
       launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
       SpmvArgs<T, int32_t> a{bufptr<int32_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, halo_ptr, (int)n_local, y, w,
-                             bufptr<T>(partials) + 2 * part_off, c->gate, c->gate_value,
+                             bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
                              bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w};
       launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
@@ -780,17 +763,7 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
 
 template <typename T>
 void CsrMat<T>::finalize_epilogue(bool allreduce) {
-  {
-    LaunchScope ls(ctx, FAM_SCALAR);
-    if (allreduce && peer_mode(ctx))
-      finalize_partials_kernel<T, true><<<1, 256, 0, ctx->stream>>>(bufptr<T>(partials), last_partial_blocks,
-                                                                    bufptr<scal2>(red), ctx->dist->scal->ptrs());
-    else
-      finalize_partials_kernel<T, false><<<1, 256, 0, ctx->stream>>>(bufptr<T>(partials), last_partial_blocks,
-                                                                     bufptr<scal2>(red), PeerPtrs{});
-    check_launch("finalize_partials_kernel");
-  }
-  if (allreduce && !peer_mode(ctx)) allreduce_sum(ctx, (double*)bufptr<scal2>(red), 4);
+  finalize_reduce<T>(ctx, bufptr<Acc<T>>(partials), last_partial_blocks, bufptr<scal2>(red), allreduce);
 }
 
 template <typename T>

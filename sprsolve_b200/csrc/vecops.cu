@@ -8,59 +8,97 @@
 
 namespace spb {
 
-// PEER: the sum over ranks happens in the same CTA through the peers' scalar windows (peer.cuh).
-template <typename T, bool PEER>
-__global__ void finalize_partials_k(const T* partials, int64_t nblocks, scal2* red, PeerPtrs pp) {
-  __shared__ T scratch[32];
-  __shared__ double loc[4];
+// Finishes a reduction point: fixed-order double-double sum of the block partials (reduce.cuh), the
+// sum over the ranks, ONE rounding to double.  MODE 0: this rank only; MODE 1: the sum over ranks
+// happens in the same CTA through the peers' scalar windows (peer.cuh); MODE 2 (NCCL transport):
+// the unrounded pairs are written to dd_out, all-gathered, and finish_gathered_k sums and rounds.
+template <typename T, int MODE>
+__global__ void finalize_reduce_k(const Acc<T>* partials, int64_t nblocks, scal2* red, PeerPtrs pp, double* dd_out) {
+  __shared__ Acc<T> scratch[32];
+  __shared__ double loc[8];
+  __shared__ double fin[4];
+  const int t = threadIdx.x;
   for (int slot = 0; slot < 2; ++slot) {
-    const T s = block_sum_partials(partials + slot, nblocks, 2, scratch);
-    if (threadIdx.x == 0) {
-      const scal2 v = to_scal2(s);
-      loc[2 * slot] = v.re;
-      loc[2 * slot + 1] = v.im;
+    const Acc<T> s = block_sum_partials(partials + slot, nblocks, 2, scratch);
+    if (t == 0) acc_store(s, loc + 4 * slot);
+  }
+  if (MODE == 1) {
+    peer_allreduce_dd(loc, pp);
+    if (t < 4) fin[t] = loc[t];
+  } else {
+    __syncthreads();
+    if (MODE == 2) {
+      if (t < 8) dd_out[t] = loc[t];
+      return;
     }
+    if (t < 4) fin[t] = loc[2 * t] + loc[2 * t + 1];
   }
-  if (PEER) peer_allreduce4(loc, pp);
-  else __syncthreads();
-  if (threadIdx.x < 2) red[threadIdx.x] = scal2{loc[2 * threadIdx.x], loc[2 * threadIdx.x + 1]};
+  __syncthreads();
+  if (t < 2) red[t] = scal2{fin[2 * t], fin[2 * t + 1]};
+}
+
+// NCCL transport: gathered = [world][8]; rank-order double-double sum of every pair, one rounding.
+__global__ void finish_gathered_k(const double* gathered, int world, scal2* red) {
+  __shared__ double fin[4];
+  const int t = threadIdx.x;
+  if (t < 4) {
+    double hi = 0.0, lo = 0.0;
+    for (int q = 0; q < world; ++q) {
+      lo += gathered[8 * q + 2 * t + 1];
+      dd_add(hi, lo, gathered[8 * q + 2 * t]);
+    }
+    fin[t] = hi + lo;
+  }
+  __syncthreads();
+  if (t < 2) red[t] = scal2{fin[2 * t], fin[2 * t + 1]};
 }
 
 template <typename T>
-void finalize_partials(Ctx* c, const T* partials, int64_t nblocks, scal2* red) {
+void finalize_reduce(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2* red, bool allreduce) {
+  const bool dist = allreduce && c->dist && c->dist->world > 1;
   LaunchScope ls(c, FAM_SCALAR);
-  finalize_partials_k<T, false><<<1, 256, 0, c->stream>>>(partials, nblocks, red, PeerPtrs{});
-  check_launch("finalize_partials");
+  if (!dist) {
+    finalize_reduce_k<T, 0><<<1, 256, 0, c->stream>>>(partials, nblocks, red, PeerPtrs{}, nullptr);
+  } else if (peer_mode(c)) {
+    finalize_reduce_k<T, 1><<<1, 256, 0, c->stream>>>(partials, nblocks, red, c->dist->scal->ptrs(), nullptr);
+  } else {
+    Dist* d = c->dist;
+    d->dd_buf.ensure(sizeof(double) * 8 * (size_t)(d->world + 1));
+    double* send = bufptr<double>(d->dd_buf);
+    double* recv = send + 8;
+    finalize_reduce_k<T, 2><<<1, 256, 0, c->stream>>>(partials, nblocks, red, PeerPtrs{}, send);
+    SPB_NCCL(nccl().AllGather(send, recv, 8, ncclFloat64, d->comm, c->stream));
+    finish_gathered_k<<<1, 32, 0, c->stream>>>(recv, d->world, red);
+  }
+  check_launch("finalize_reduce");
 }
 
 template <typename T>
-void finalize_allreduce(Ctx* c, const T* partials, int64_t nblocks, scal2* red) {
-  if (!peer_mode(c)) {
-    finalize_partials<T>(c, partials, nblocks, red);
-    allreduce_sum(c, (double*)red, 4);
-    return;
-  }
-  LaunchScope ls(c, FAM_SCALAR);
-  finalize_partials_k<T, true><<<1, 256, 0, c->stream>>>(partials, nblocks, red, c->dist->scal->ptrs());
-  check_launch("finalize_allreduce");
+void finalize_partials(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2* red) {
+  finalize_reduce<T>(c, partials, nblocks, red, false);
+}
+
+template <typename T>
+void finalize_allreduce(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2* red) {
+  finalize_reduce<T>(c, partials, nblocks, red, true);
 }
 
 template <typename T, int KIND>
-__global__ void __launch_bounds__(kVecThreads) vec_reduce_k(int64_t n, const T* x, const T* y, T* partials) {
-  T e0 = zero_of<T>();
+__global__ void __launch_bounds__(kVecThreads) vec_reduce_k(int64_t n, const T* x, const T* y, Acc<T>* partials) {
+  Acc<T> e0 = zero_of<Acc<T>>();
   SPB_GRID_STRIDE(i, n) {
     if (KIND == 0)
-      e0 = add(e0, mul(x[i], y[i]));
+      acc_prod(e0, x[i], y[i]);           // dot, vecalg.rs:557-561
     else if (KIND == 1)
-      e0 = add(e0, mul(conj_of(x[i]), y[i]));
+      acc_prod(e0, conj_of(x[i]), y[i]);  // conj_dot, :564-568
     else
-      e0 = add(e0, from_real<T>(square(x[i])));
+      acc_sq(e0, x[i]);                   // norm2 squared, :601-605
   }
-  write_partials(e0, zero_of<T>(), partials);
+  write_partials(e0, zero_of<Acc<T>>(), partials);
 }
 
 template <typename T>
-void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, T* partials, scal2* red) {
+void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, Acc<T>* partials, scal2* red, bool allreduce) {
   const int grid = vec_grid(c, n);
   {
     LaunchScope ls(c, FAM_VEC);
@@ -72,7 +110,7 @@ void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, T* partials
       vec_reduce_k<T, 2><<<grid, kVecThreads, 0, c->stream>>>(n, x, y, partials);
     check_launch("vec_reduce");
   }
-  finalize_partials<T>(c, partials, grid, red);
+  finalize_reduce<T>(c, partials, grid, red, allreduce);
 }
 
 template <typename T>
@@ -133,9 +171,10 @@ void vec_zero(Ctx* c, int64_t n, T* x) {
 }
 
 #define SPB_INST(T)                                                                          \
-  template void finalize_partials<T>(Ctx*, const T*, int64_t, scal2*);                       \
-  template void finalize_allreduce<T>(Ctx*, const T*, int64_t, scal2*);                      \
-  template void vec_reduce<T>(Ctx*, int, int64_t, const T*, const T*, T*, scal2*);           \
+  template void finalize_reduce<T>(Ctx*, const Acc<T>*, int64_t, scal2*, bool);              \
+  template void finalize_partials<T>(Ctx*, const Acc<T>*, int64_t, scal2*);                  \
+  template void finalize_allreduce<T>(Ctx*, const Acc<T>*, int64_t, scal2*);                 \
+  template void vec_reduce<T>(Ctx*, int, int64_t, const T*, const T*, Acc<T>*, scal2*, bool); \
   template void vec_axpy<T>(Ctx*, int64_t, T, const T*, T*);                                 \
   template void vec_axpby<T>(Ctx*, int64_t, T, const T*, T, T*);                             \
   template void vec_scale<T>(Ctx*, int64_t, T, T*);                                          \

@@ -32,17 +32,20 @@ __device__ __forceinline__ void write_partials(T e0, T e1, T* partials) {
   }
 }
 
-// Fixed-order sum of the block partials into red[0], red[1] (one tiny CTA).
+// Fixed-order double-double sum of the block partials, rounded once, into red[0], red[1] (one tiny
+// CTA).  allreduce: followed by the sum over ranks before the rounding (fused into the same kernel
+// on the peer transport; all-gather of the unrounded pairs on the NCCL transport).
 template <typename T>
-void finalize_partials(Ctx* c, const T* partials, int64_t nblocks, scal2* red);
-// Same, followed by the sum over ranks (fused into the same kernel on the peer transport).
+void finalize_reduce(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2* red, bool allreduce);
 template <typename T>
-void finalize_allreduce(Ctx* c, const T* partials, int64_t nblocks, scal2* red);
+void finalize_partials(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2* red);
+template <typename T>
+void finalize_allreduce(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2* red);
 
 // vecalg on device pointers ---------------------------------------------------------------
 // kind: 0 = dot (no conjugate, vecalg.rs:557-561), 1 = conj_dot (:564-568), 2 = sum |x|^2 (:601-605)
 template <typename T>
-void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, T* partials, scal2* red);
+void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, Acc<T>* partials, scal2* red, bool allreduce = false);
 template <typename T>
 void vec_axpy(Ctx* c, int64_t n, T a, const T* x, T* y);
 template <typename T>

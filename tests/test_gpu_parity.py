@@ -648,6 +648,31 @@ def test_bicgstab_restart_path(sp, orc):
     assert np.isfinite(x).all() == np.isfinite(o.x).all()
 
 
+def test_results_do_not_depend_on_the_launch_plan(sp, orc, monkeypatch):
+    """The fused dot products are summed in double-double and rounded once (csrc/reduce.cuh), so the
+    SpMV launch plan (tile boundaries, CTA count), the dictionary format and the grid size leave no
+    trace: residual histories and solutions are bit-identical across plans."""
+    A = orc.gen_convdiff27(20, 18, 16)
+    rhs = orc.spmv(A, np.ones(A.n))
+    runs = []
+    for knobs in ({}, {"SPB_SPMV_CT": "32", "SPB_SPMV_STAGES": "1", "SPB_SPMV_MAXTILE": "512"}, {"SPB_SPMV_CT": "256", "SPB_SPMV_STAGES": "3"},
+                  {"SPB_SPMV_DICT": "0"}, {"SPB_SPMV_DICT": "0", "SPB_SPMV_CT": "96", "SPB_SPMV_BPS": "2"}):
+        for k in [k for k in os.environ if k.startswith("SPB_SPMV_")]:
+            monkeypatch.delenv(k)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        G = to_gpu(sp, A)
+        S = sp.BiCGStab(G, A.n).record_history(600)
+        x = np.zeros(A.n)
+        it, res = S.precond_solve(sp.DiagPrecond.from_matrix(G), rhs, x, 500, 1e-8)
+        y = np.zeros(A.n)
+        d = G.mul_vec_dot(rhs, y)
+        runs.append((it, res, S.history.copy(), x, d))
+    for r in runs[1:]:
+        assert r[0] == runs[0][0] and r[1] == runs[0][1] and r[4] == runs[0][4]
+        assert np.array_equal(r[2], runs[0][2]) and np.array_equal(r[3], runs[0][3])
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_spmv_config2_full_size_properties(sp):
     """Config C2 (256^3 7-point): size-independent properties instead of an oracle run:

@@ -132,6 +132,14 @@ def test_partitioned_parity(orc, transport):
     x = np.concatenate([got[r]["bicg"][3] for r in range(world)])
     floor, it_range = _noise_floor(orc, "bicgstab", A, rhs, pc, 1e-8, 500, o)
     _check_solve(((it, rr, x, hist), o, floor, it_range), 1e-8, A, rhs, xs=np.ones(n))
+    # ... and bit for bit the single-GPU solve: SpMV and the vector updates are element-wise
+    # identical, the reductions are order-independent (double-double, csrc/reduce.cuh), so the
+    # partition of the rows leaves no trace in the iterates.
+    G1 = sp.GpuCsrMat.new(A.indptr, A.indices, A.data)
+    S1 = sp.BiCGStab(G1, n).record_history(600)
+    x1 = np.zeros(n)
+    it1, rr1 = S1.precond_solve(sp.DiagPrecond.from_matrix(G1), rhs, x1, 500, 1e-8)
+    assert it1 == it and rr1 == rr and np.array_equal(S1.history, hist) and np.array_equal(x1, x)
     # MINRES vs the serial oracle (well conditioned w.r.t. summation order: strict 1e-10 / +-2 %)
     A3 = orc.gen_lap3d7(G, shift=0.05)
     rhs3 = orc.spmv(A3, np.ones(n))
@@ -141,3 +149,8 @@ def test_partitioned_parity(orc, transport):
     x3 = np.concatenate([got[r]["minres"][3] for r in range(world)])
     floor3, range3 = _noise_floor(orc, "minres", A3, rhs3, None, 1e-8, 500, o3)
     _check_solve(((it3, rr3, x3, h3), o3, floor3, range3), 1e-8, A3, rhs3, strict=True, xs=np.ones(n))
+    G3 = sp.GpuCsrMat.new(A3.indptr, A3.indices, A3.data)
+    S3 = sp.MinRes(G3, n).record_history(600)
+    x31 = np.zeros(n)
+    it31, rr31 = S3.solve(rhs3, x31, 500, 1e-8)
+    assert it31 == it3 and rr31 == rr3 and np.array_equal(S3.history, h3) and np.array_equal(x31, x3)
