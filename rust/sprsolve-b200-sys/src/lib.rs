@@ -58,6 +58,8 @@ extern "C" {
         values: *const c_void, out: *mut *mut spb_op,
     ) -> c_int;
     pub fn spb_csr_read_matrix_market(ctx: *mut spb_ctx, dtype: c_int, path: *const c_char, out: *mut *mut spb_op) -> c_int;
+    pub fn spb_csr_plan_info(mat: *mut spb_op, info: *mut i64) -> c_int; // [8]
+    pub fn spb_gs_schedule_info(gs: *mut spb_op, info: *mut i64, stats: *mut i64, stats_cap: i64) -> c_int; // info [16]
     pub fn spb_csr_mv_hint(mat: *mut spb_op, ncalls: c_int) -> c_int;
     pub fn spb_csr_mv_and_dotmv_hint(mat: *mut spb_op, ncalls: c_int) -> c_int;
     pub fn spb_op_destroy(op: *mut spb_op) -> c_int;

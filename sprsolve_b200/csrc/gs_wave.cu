@@ -745,12 +745,9 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
 }
 
 template <typename T, typename IP>
-static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out) {
+static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other) {
   Ctx* c = M->ctx;
   CsrMat<T>* A = M->A;
-  const int64_t n = A->n_local;
-  (void)n;
-  (void)out;
   const int64_t mb8 = ws.mailbox_slots * (int64_t)(sizeof(T) / 8);
   const int64_t work = std::max(mb8, ws.rhs_slots);
   LaunchScope lsc(c, FAM_PRECOND);
@@ -771,9 +768,9 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   const int oth_bytes = wave_a16((long long)sizeof(T) * ws.stage_other);
   const int stage_bytes = (ws.stage_static + rhs_bytes + oth_bytes + 127) / 128 * 128;
   if (M->A->ip64)
-    wave_prep_launch<T, int64_t>(M, ws, rhs, other, out);
+    wave_prep_launch<T, int64_t>(M, ws, rhs, other);
   else
-    wave_prep_launch<T, int32_t>(M, ws, rhs, other, out);
+    wave_prep_launch<T, int32_t>(M, ws, rhs, other);
   WaveArgs<T> a{};
   a.stat = bufptr<unsigned char>(ws.stat);
   a.chunks = bufptr<WaveChunk>(ws.chunks);
