@@ -42,6 +42,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "ops.cuh"
@@ -623,92 +625,118 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   }
 
   lap("mail lists");
-  // ---- pass B: emit the packed chunks ----------------------------------------------------------
-  std::vector<int> slot_of(n, -1);  // column -> slot inside the chunk being emitted
-  for (size_t ci = 0; ci < plans.size(); ++ci) {
+  // ---- pass B: emit the packed chunks.  Output extents first (cheap, sequential), then the
+  //      chunks are filled by a few host threads: every chunk owns disjoint ranges of every array.
+  const size_t nplans = plans.size();
+  std::vector<size_t> stat_off(nplans + 1, 0);
+  std::vector<int64_t> slot_off(nplans + 1, 0), auxo(nplans, 0);
+  std::vector<int> wm_of(nplans, 0);
+  for (size_t ci = 0; ci < nplans; ++ci) {
     const Plan& pl = plans[ci];
     const int nrows = pl.row_end - pl.row_beg, nseg = pl.seg_end - pl.seg_beg, nhalo = pl.hal_end - pl.hal_beg;
-    const int W = pl.W, Wo = pl.Wo;
-    const int64_t first = plan_rows[pl.row_beg];
-    const int64_t r0 = (first / R) * R, r1 = std::min(n, r0 + R);
     int Wm = 0;
     for (int q = 0; q < nrows; ++q) {
       const int64_t i = plan_rows[pl.row_beg + q];
       Wm = std::max<int>(Wm, (int)(mail_ptr[i + 1] - mail_ptr[i]));
     }
-    const WaveLayout L = wave_layout<T>(nrows, nseg, W, nhalo, Wm);
+    wm_of[ci] = Wm;
+    const WaveLayout L = wave_layout<T>(nrows, nseg, pl.W, nhalo, Wm);
     if (L.total > ws.stage_static) return;  // cannot happen: Wm <= the estimate used in pass A
-    const size_t base = stat.size();
-    stat.resize(base + L.total, 0);
-    const uint32_t stage_base = (uint32_t)(ring_off + (size_t)(pl.kblk % ws.stages) * stage_bytes);
-    WaveChunk d{};
-    d.soff = (long long)base;
-    d.sbytes = L.total;
-    d.nrows = nrows;
-    d.rhs_off = (long long)rowmap.size();
+    stat_off[ci + 1] = stat_off[ci] + (size_t)L.total;
+    slot_off[ci + 1] = align_slots(slot_off[ci] + nrows);
     if (backward) {
-      d.aux_off = d.rhs_off;  // one pre-folded value per row, same slots as rhs
-      d.aux_cnt = nrows;
+      auxo[ci] = slot_off[ci];  // one pre-folded value per row, same slots as rhs
     } else {
-      d.aux_off = aux_slots;
-      d.aux_cnt = Wo * nrows;
-      aux_slots = align_slots(aux_slots + d.aux_cnt);
+      auxo[ci] = aux_slots;
+      aux_slots = align_slots(aux_slots + (int64_t)pl.Wo * nrows);
     }
-    for (int h = 0; h < nhalo; ++h) slot_of[plan_halo[pl.hal_beg + h]] = h;
-    std::vector<uint32_t> eoff((size_t)W * nrows, (uint32_t)WAVE_ZERO_OFF), mail((size_t)Wm * nrows, SPB_WAVE_NOMAIL);
-    std::vector<T> ev((size_t)W * nrows, zero_of<T>()), dg(nrows), hs(nhalo);
-    for (int h = 0; h < nhalo; ++h) {
-      unsigned long long w[2] = {sentinel, sentinel};
-      memcpy(&hs[h], w, sizeof(T));
-    }
-    for (int q = 0; q < nrows; ++q) {
-      const int64_t i = plan_rows[pl.row_beg + q];
-      int e = 0;
-      T dv = zero_of<T>();
-      for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
-        const int j = cols[k];
-        if (j == i) {
-          dv = vals[k];  // the last diagonal entry wins, as in the loop of src/gauss_seidel.rs:119-121
-          continue;
+  }
+  stat.assign(stat_off[nplans], 0);
+  chunks.assign(nplans, WaveChunk{});
+  rowmap.assign((size_t)slot_off[nplans], -1);
+  if (!backward) {
+    aux_base.assign((size_t)slot_off[nplans], 0);
+    aux_dims.assign(2 * (size_t)slot_off[nplans], 0);
+  }
+  auto emit_range = [&](size_t c_begin, size_t c_end) {
+    std::vector<std::pair<int, int>> halo_slot;  // (column, slot) of the chunk, sorted by column
+    for (size_t ci = c_begin; ci < c_end; ++ci) {
+      const Plan& pl = plans[ci];
+      const int nrows = pl.row_end - pl.row_beg, nseg = pl.seg_end - pl.seg_beg, nhalo = pl.hal_end - pl.hal_beg;
+      const int W = pl.W, Wo = pl.Wo, Wm = wm_of[ci];
+      const int64_t first = plan_rows[pl.row_beg];
+      const int64_t r0 = (first / R) * R, r1 = std::min(n, r0 + R);
+      const WaveLayout L = wave_layout<T>(nrows, nseg, W, nhalo, Wm);
+      const size_t base = stat_off[ci];
+      const uint32_t stage_base = (uint32_t)(ring_off + (size_t)(pl.kblk % ws.stages) * stage_bytes);
+      WaveChunk d{};
+      d.soff = (long long)base;
+      d.sbytes = L.total;
+      d.nrows = nrows;
+      d.rhs_off = (long long)slot_off[ci];
+      d.aux_off = (long long)auxo[ci];
+      d.aux_cnt = backward ? nrows : Wo * nrows;
+      halo_slot.clear();
+      for (int h = 0; h < nhalo; ++h) halo_slot.emplace_back(plan_halo[pl.hal_beg + h], h);
+      std::sort(halo_slot.begin(), halo_slot.end());
+      std::vector<uint32_t> eoff((size_t)W * nrows, (uint32_t)WAVE_ZERO_OFF), mail((size_t)Wm * nrows, SPB_WAVE_NOMAIL);
+      std::vector<T> ev((size_t)W * nrows, zero_of<T>()), dg(nrows), hs(nhalo);
+      for (int h = 0; h < nhalo; ++h) {
+        unsigned long long w[2] = {sentinel, sentinel};
+        memcpy(&hs[h], w, sizeof(T));
+      }
+      for (int q = 0; q < nrows; ++q) {
+        const int64_t i = plan_rows[pl.row_beg + q];
+        int e = 0;
+        T dv = zero_of<T>();
+        for (int64_t k = ip[i]; k < ip[i + 1]; ++k) {
+          const int j = cols[k];
+          if (j == i) {
+            dv = vals[k];  // the last diagonal entry wins, as in the loop of src/gauss_seidel.rs:119-121
+            continue;
+          }
+          if (!(backward ? (j > i) : (j < i))) continue;  // other triangle: handled by the pre-pass
+          uint32_t off;
+          if (j >= r0 && j < r1) {
+            off = (uint32_t)(WAVE_FIXED + (size_t)(j - r0) * sizeof(T));
+          } else {
+            const auto it = std::lower_bound(halo_slot.begin(), halo_slot.end(), std::make_pair(j, 0));
+            off = stage_base + (uint32_t)L.hslot + (uint32_t)(it->second * sizeof(T));
+          }
+          eoff[(size_t)e * nrows + q] = off;
+          ev[(size_t)e * nrows + q] = vals[k];
+          ++e;
         }
-        if (!(backward ? (j > i) : (j < i))) continue;  // other triangle: handled by the pre-pass
-        uint32_t off;
-        if (j >= r0 && j < r1)
-          off = (uint32_t)(WAVE_FIXED + (size_t)(j - r0) * sizeof(T));
-        else
-          off = stage_base + (uint32_t)L.hslot + (uint32_t)(slot_of[j] * sizeof(T));
-        eoff[(size_t)e * nrows + q] = off;
-        ev[(size_t)e * nrows + q] = vals[k];
-        ++e;
+        dg[q] = dv;
+        int m = 0;
+        for (int64_t k = mail_ptr[i]; k < mail_ptr[i + 1]; ++k) mail[(size_t)(m++) * nrows + q] = mail_idx[(size_t)k];
+        const size_t slot = (size_t)slot_off[ci] + q;
+        rowmap[slot] = (int)i;
+        if (!backward) {
+          aux_base[slot] = d.aux_off + q;
+          aux_dims[2 * slot] = nrows;
+          aux_dims[2 * slot + 1] = Wo;
+        }
       }
-      dg[q] = dv;
-      int m = 0;
-      for (int64_t k = mail_ptr[i]; k < mail_ptr[i + 1]; ++k) mail[(size_t)(m++) * nrows + q] = mail_idx[(size_t)k];
-      rowmap.push_back((int)i);
-      if (!backward) {
-        aux_base.push_back(d.aux_off + q);
-        aux_dims.push_back(nrows);
-        aux_dims.push_back(Wo);
-      }
+      const int hdr[8] = {nrows, nseg, W, nhalo, Wo, Wm, (int)(unsigned)(pl.mb_off & 0xffffffffLL), (int)(pl.mb_off >> 32)};
+      put_bytes(stat, base, hdr, 8);
+      put_bytes(stat, base + L.seg_end, plan_segs.data() + pl.seg_beg, nseg);
+      put_bytes(stat, base + L.rowid, plan_rows.data() + pl.row_beg, nrows);
+      put_bytes(stat, base + L.diag, dg.data(), nrows);
+      put_bytes(stat, base + L.eoff, eoff.data(), eoff.size());
+      put_bytes(stat, base + L.eval, ev.data(), ev.size());
+      put_bytes(stat, base + L.mail, mail.data(), mail.size());
+      put_bytes(stat, base + L.hslot, hs.data(), hs.size());
+      chunks[ci] = d;
     }
-    while ((int64_t)rowmap.size() != align_slots((int64_t)rowmap.size())) {
-      rowmap.push_back(-1);
-      if (!backward) {
-        aux_base.push_back(0);
-        aux_dims.push_back(0);
-        aux_dims.push_back(0);
-      }
-    }
-    const int hdr[8] = {nrows, nseg, W, nhalo, Wo, Wm, (int)(unsigned)(pl.mb_off & 0xffffffffLL), (int)(pl.mb_off >> 32)};
-    put_bytes(stat, base, hdr, 8);
-    put_bytes(stat, base + L.seg_end, plan_segs.data() + pl.seg_beg, nseg);
-    put_bytes(stat, base + L.rowid, plan_rows.data() + pl.row_beg, nrows);
-    put_bytes(stat, base + L.diag, dg.data(), nrows);
-    put_bytes(stat, base + L.eoff, eoff.data(), eoff.size());
-    put_bytes(stat, base + L.eval, ev.data(), ev.size());
-    put_bytes(stat, base + L.mail, mail.data(), mail.size());
-    put_bytes(stat, base + L.hslot, hs.data(), hs.size());
-    chunks.push_back(d);
+  };
+  {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::max<size_t>(1, std::min<size_t>({(size_t)8, (size_t)hw / 2 + 1, nplans / 64 + 1}));
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < nt; ++k) pool.emplace_back(emit_range, nplans * k / nt, nplans * (k + 1) / nt);
+    emit_range(0, nplans / nt);
+    for (auto& th : pool) th.join();
   }
   lap("pass B");
   blk_chunk[nb] = (int)chunks.size();

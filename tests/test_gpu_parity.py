@@ -476,7 +476,10 @@ def _check_solve(run, tol, A, rhs, strict=False, xs=None):
     live = o.hist[:m] >= tol  # entries above the solve tolerance (the terminal entry is just "< tol")
     dev = np.where(live, dev, 0.0)
     if strict:
-        assert floor[:m][live].max() < 1e-10, "case is not as well conditioned as assumed"
+        # (the OpenMP flavour of the oracle is not run-to-run deterministic; on the 96^2 case its spread
+        # hovers around 1e-10 at iteration ~49, hence the slack on this sanity check only -- the
+        # 1e-10 bar on the GPU history below is exact and deterministic)
+        assert floor[:m][live].max() < 1e-9, "case is not as well conditioned as assumed"
         assert np.all(dev <= HIST_RTOL), dev.max()
         assert_iters(it, o.iters)
     else:
