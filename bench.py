@@ -9,17 +9,25 @@ Workload (config.workload): BASELINE.json configs[4] -- Jacobi-preconditioned Bi
 the row-partitioned 3-D 27-point convection-diffusion system 512^3 (134,217,728 rows,
 3,609,741,304 non-zeros), rhs = A*1, x0 = 0.  It fits one B200 (56 GB), so it is also the N=1
 workload; total work is fixed as N grows (scaling: strong, as the north star's "6x faster on 8
-GPUs than on 1" demands).  A "step" is one solver call capped at --iters BiCGStab iterations
-starting from x0 = 0 (every iteration does identical work: 2 SpMV + 3 fused vector kernels +
-3 reduction points); one full solve to rtol 1e-8 is run first and reported in `full_solve`.
+GPUs than on 1" demands).  A "step" is one solver call capped at --iters (default 100) BiCGStab
+iterations starting from x0 = 0 (every iteration does identical work: 2 SpMV + 3 fused vector
+kernels + 3 reduction points; a full solve of this system takes 640); one full solve to rtol
+1e-8 is run first and reported in `full_solve` (its iteration count and final residual are the
+same at every GPU count: the reductions are order-independent, csrc/reduce.cuh).
 
 value   : iterations/s with rhs / x resident in HBM (spb_solver_solve_dev), CUDA events on the
           launching stream, barrier + synchronize on both sides, max over ranks.
 e2e     : the same through the host-buffer path: each step copies rhs and x0 from pinned host
-          memory to the device, solves, and copies x back (h2d/d2h bytes per step reported).
+          memory to the device, solves, and copies x back (h2d/d2h bytes per step reported); the
+          caller-side zeroing of the initial guess happens before the timed region (one pinned x
+          buffer per step).
 roofline: the SpMV kernel (dominant: ~80 % of an iteration's bytes), algorithmic bytes
           nnz*12 + (n+1)*sizeof(indptr) + 2*n*8 per launch (per rank) / average launch duration
           measured live with CUDA events around every SpMV launch of one extra profiled step.
+          `achieved` / `frac` use those ALGORITHMIC bytes (the plain CSR stream of the reference's
+          operator); when the analysis replaces the column stream by the row-pattern dictionary the
+          kernel moves fewer bytes (`stream_bytes_per_launch`, `stream_gbs`, `stream_frac` -- what
+          the HBM roofline actually bounds), so `frac` can exceed 1.
 spmv_c2 : BASELINE.json configs[1], standalone SpMV on the 3-D 7-point 256^3 matrix (N=1 only).
 cpu_baseline / --impl reference: the reference cannot be built here (Rust nightly + MKL +
           unvendored git deps, no cargo), so the CPU arm is the oracle port of its solver loop
