@@ -16,6 +16,7 @@
 //   K3 : x -= alpha y ; x -= w z ; r -= w t ; partials of ||r||^2 and <r0,r>      (:355-362,296,301)
 // n-vector streams per iteration: K1 4R+2W, SpMV1 epilogue 1R, K2 3R+2W, SpMV2 epilogue 1R,
 // K3 6R+2W = 21 (Jacobi); 16 without preconditioner.
+#include "finalize.cuh"
 #include "solver.cuh"
 
 namespace spb {
@@ -96,7 +97,7 @@ __global__ void bicg_s1(BicgState<T>* st, const scal2* red, double* hist, long l
 }
 
 template <typename T>
-__global__ void bicg_s2(BicgState<T>* st, const scal2* red, int first) {
+__device__ __forceinline__ void bicg_s2_body(BicgState<T>* st, const scal2* red, int first) {
   if (st->h.status != DS_RUNNING) return;
   const T tmp = from_scal2<T>(red[0]);  // conj_dot(r0, v), :332
   if (!first && abs_of(tmp) <= 0.0) {   // :333-336 (the unrolled first iteration has no test, :266)
@@ -107,14 +108,29 @@ __global__ void bicg_s2(BicgState<T>* st, const scal2* red, int first) {
   st->alpha = divi(st->rho, tmp);  // :338
   st->nalpha = neg(st->alpha);
 }
+// fused into the kernel that finishes <r0, v> (finalize.cuh)
+template <typename T>
+struct BicgS2Tail {
+  BicgState<T>* st;
+  const scal2* red;
+  int first;
+  __device__ __forceinline__ void operator()() const { bicg_s2_body(st, red, first); }
+};
 
 template <typename T>
-__global__ void bicg_s3(BicgState<T>* st, const scal2* red) {
+__device__ __forceinline__ void bicg_s3_body(BicgState<T>* st, const scal2* red) {
   if (st->h.status != DS_RUNNING) return;
   const T tt = from_scal2<T>(red[0]);  // conj_dot(t, t), :347
   st->w = re_of(tt) > 0.0 ? divi(from_scal2<T>(red[1]), tt) : zero_of<T>();  // :348-352
   st->nw = neg(st->w);
 }
+// fused into the kernel that finishes <t, t>, <t, r>
+template <typename T>
+struct BicgS3Tail {
+  BicgState<T>* st;
+  const scal2* red;
+  __device__ __forceinline__ void operator()() const { bicg_s3_body(st, red); }
+};
 
 // ---------------------------------------------------------------- vector kernels
 template <typename T>
@@ -258,8 +274,8 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   auto reduce_vec = [&]() {  // per-block partials of a vector kernel -> red (all ranks)
     finalize_allreduce<T>(c, parts, grid, redp);
   };
-  auto reduce_spmv = [&]() {
-    Am->finalize_epilogue(true);
+  auto reduce_spmv = [&](auto tail) {  // epilogue partials of the last SpMV -> Am->red (all ranks), then the scalar step
+    finalize_reduce_tail<T>(c, bufptr<Acc<T>>(Am->partials), Am->last_partial_blocks, bufptr<scal2>(Am->red), true, tail);
   };
   auto k_init = [&](int restart) {
     LaunchScope ls(c, FAM_VEC);
@@ -296,12 +312,10 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   auto tail = [&](bool first) {  // everything of an iteration after the S1 test
     k1(first);
     Am->mul(y, v, EPI_DOT_WY, r0, false);
-    reduce_spmv();
-    scalar(bicg_s2<T>, st, bufptr<scal2>(Am->red), first ? 1 : 0);
+    reduce_spmv(BicgS2Tail<T>{st, bufptr<scal2>(Am->red), first ? 1 : 0});  // + alpha = rho / <r0, v>
     k2();
     Am->mul(z, t, EPI_TT_TR, r, false);
-    reduce_spmv();
-    scalar(bicg_s3<T>, st, bufptr<scal2>(Am->red));
+    reduce_spmv(BicgS3Tail<T>{st, bufptr<scal2>(Am->red)});                 // + w = <t, r> / <t, t>
     {
       LaunchScope ls(c, FAM_VEC);
       bicg_k3<T><<<grid, kVecThreads, 0, c->stream>>>(st, n, x, y, z, r, t, r0, parts);

@@ -11,6 +11,7 @@
 //   S    : beta_new, Givens rotation, residual estimate, convergence          (minres.rs:120-148,164-168)
 //   KM2  : v_new *= 1/beta_new ; p = (q - r2 p_old - r3 p_oold) r1_inv ; x += tau p   (:121,151-162)
 // n-vector streams per iteration: SpMV epilogue 1R, KM1 3R+1W, KM2 5R+3W = 13.
+#include "finalize.cuh"
 #include "solver.cuh"
 
 namespace spb {
@@ -72,17 +73,24 @@ __global__ void mr_s_init(MinresState<T>* st, const scal2* red, const scal2* b2,
 }
 
 template <typename T>
-__global__ void mr_s_alpha(MinresState<T>* st, const scal2* red) {
+__device__ __forceinline__ void mr_s_alpha_body(MinresState<T>* st, const scal2* red) {
   if (st->h.status != DS_RUNNING) return;
   st->beta = st->beta_new;               // :91
   st->alpha = from_scal2<T>(red[0]);     // :116
   st->nalpha = neg(st->alpha);
   st->nbeta = from_real<T>(-st->beta);   // T::from_real(-beta), :117
 }
+// fused into the kernel that finishes alpha = <q, A q> (finalize.cuh)
+template <typename T>
+struct MrAlphaTail {
+  MinresState<T>* st;
+  const scal2* red;
+  __device__ __forceinline__ void operator()() const { mr_s_alpha_body(st, red); }
+};
 
 template <typename T, bool CS>
-__global__ void mr_s_givens(MinresState<T>* st, const scal2* red, const scal2* b2, int precond,
-                            long long its, double* hist, long long cap) {
+__device__ __forceinline__ void mr_s_givens_body(MinresState<T>* st, const scal2* red, const scal2* b2, int precond,
+                                                 long long its, double* hist, long long cap) {
   if (st->h.status != DS_RUNNING) return;
   double beta_new;
   if (precond) {
@@ -124,6 +132,23 @@ __global__ void mr_s_givens(MinresState<T>* st, const scal2* red, const scal2* b
   }
   st->eta = mul_real(st->eta, -s_new);  // :168
 }
+template <typename T, bool CS>
+__global__ void mr_s_givens(MinresState<T>* st, const scal2* red, const scal2* b2, int precond, long long its, double* hist,
+                            long long cap) {
+  mr_s_givens_body<T, CS>(st, red, b2, precond, its, hist, cap);
+}
+// fused into the kernel that finishes ||v_new||^2 (and <v_new, w_new> with Jacobi)
+template <typename T, bool CS>
+struct MrGivensTail {
+  MinresState<T>* st;
+  const scal2* red;
+  const scal2* b2;
+  int precond;
+  long long its;
+  double* hist;
+  long long cap;
+  __device__ __forceinline__ void operator()() const { mr_s_givens_body<T, CS>(st, red, b2, precond, its, hist, cap); }
+};
 
 // v_new = rhs - A x (A x is in v_old) ; ||v_new||^2 ; v = p_old = p = 0      (minres.rs:77-88)
 template <typename T, typename V, bool JACOBI>
@@ -337,8 +362,8 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
           const T* q = precond ? w : v;
           // v_new = A q with alpha = conj(q) . v_new   (CS: v_new = A conj(v), alpha = conj(v) . v_new)
           Am->mul(q, v_new, EPI_DOT_WY, q, cs);
-          Am->finalize_epilogue(true);
-          scalar(mr_s_alpha<T>, st, bufptr<scal2>(Am->red));
+          finalize_reduce_tail<T>(c, bufptr<Acc<T>>(Am->partials), Am->last_partial_blocks, bufptr<scal2>(Am->red), true,
+                                  MrAlphaTail<T>{st, bufptr<scal2>(Am->red)});  // + alpha, -beta
           {
             LaunchScope ls(c, FAM_VEC);
             if (pcm == PCM_JACOBI)
@@ -349,12 +374,16 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
               mr_k1<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)nullptr, parts);
             check_launch("mr_k1");
           }
-          reduce_vec();
-          if (pcm == PCM_GENERIC) generic_b2(v_new, w_new);
-          if (cs)
-            scalar(mr_s_givens<T, true>, st, redp, b2src, 0, (long long)its, hd, cap);
-          else
-            scalar(mr_s_givens<T, false>, st, redp, b2src, precond ? 1 : 0, (long long)its, hd, cap);
+          if (pcm == PCM_GENERIC) {  // beta^2 = <v_new, M v_new> needs the operator in between: not fused
+            reduce_vec();
+            generic_b2(v_new, w_new);
+            scalar(mr_s_givens<T, false>, st, redp, b2src, 1, (long long)its, hd, cap);
+          } else if (cs) {
+            finalize_reduce_tail<T>(c, parts, grid, redp, true, MrGivensTail<T, true>{st, redp, b2src, 0, (long long)its, hd, cap});
+          } else {
+            finalize_reduce_tail<T>(c, parts, grid, redp, true,
+                                    MrGivensTail<T, false>{st, redp, b2src, precond ? 1 : 0, (long long)its, hd, cap});
+          }
           T* pt = p_oold;
           p_oold = p_old;
           p_old = p;
