@@ -160,7 +160,8 @@ int spb_gs_levels(spb_op* gs, int64_t* n_levels_fwd, int64_t* n_levels_bwd);
 /* Block-wavefront schedule of the sweep (diagnostics): info = {fwd ok, rows per block, blocks, fwd chunks,
  * fwd local levels (max over blocks), ring stages, shared memory bytes, bwd ok, bwd chunks, bwd local levels,
  * poll-timeout flag, rhs slots, other-side slots, packed bytes, 0, 0}.  stats (optional, SPB_GS_STATS=1 at
- * create): per block of the last sweep {clocks, clocks waiting for the ring, poll retries, chunks}. */
+ * create): per block of the last sweep {clocks, clocks waiting for the ring, shared-memory spins on
+ * values of other blocks, clocks of thread 0 in the level barrier}. */
 int spb_gs_schedule_info(spb_op* gs, int64_t info[16], int64_t* stats, int64_t stats_cap);
 
 /* ---- vecalg (src/vecalg.rs:19-144) on host slices; out / a / b are (re,im) pairs -------------- */

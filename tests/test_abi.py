@@ -68,3 +68,34 @@ def test_product_never_references_the_oracle():
     assert not bad, bad
     out = subprocess.run(["ldd", os.path.join(ROOT, "sprsolve_b200", "lib", "libsprsolve_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_c_example_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/c_api_demo.c is strict C99 against include/sprsolve_b200.h (the header is a C header,
+    not only a C++ one), links against the in-tree library, and -- with no GPU in this container --
+    exits with the no-device code instead of computing anything on the CPU."""
+    import shutil
+    import subprocess
+
+    from sprsolve_b200 import build as b
+
+    lib = b.build()
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    exe = os.path.join(tmp_path, "c_api_demo")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_api_demo.c"), "-L" + os.path.dirname(lib), "-lsprsolve_b200",
+           "-Wl,-rpath," + os.path.dirname(lib), "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    run = subprocess.run([exe, "48"], capture_output=True, text=True, timeout=300)
+    if has_gpu:
+        assert run.returncode == 0 and "converged" in run.stdout, run.stdout + run.stderr
+    else:
+        assert run.returncode == 3 and "no CUDA device" in run.stdout, run.stdout + run.stderr

@@ -775,3 +775,22 @@ def test_gauss_seidel_config3_full_size_wavefront_equals_level_schedule(sp, monk
         outs.append(z)
     assert torch.equal(outs[0], outs[1])
     assert M.schedule_info()["poll_timeout"] == 0
+
+
+def test_c_example_runs(sp, tmp_path):
+    """examples/c_api_demo.c (plain C99 against the header): the reference's src/main.rs flow -- build
+    the Dirichlet Laplacian, Jacobi-BiCGStab to 1e-8 -- through the C ABI, exact solution i + j."""
+    import shutil
+    import subprocess
+
+    from sprsolve_b200 import build as b
+
+    lib = b.build()
+    exe = os.path.join(tmp_path, "c_api_demo")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([shutil.which("gcc"), "-std=c99", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "c_api_demo.c"),
+                        "-L" + os.path.dirname(lib), "-lsprsolve_b200", "-Wl,-rpath," + os.path.dirname(lib), "-lm", "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    run = subprocess.run([exe, "96"], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "converged" in run.stdout, run.stdout + run.stderr
