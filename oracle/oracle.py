@@ -60,6 +60,8 @@ def _declare(L):
     L.orc_dot_d.restype = _dbl
     L.orc_conj_dot_d.restype = _dbl
     L.orc_conj_dot_s.restype = C.c_float
+    for name in ("orc_norm2_s", "orc_norm2_c", "orc_dot_s", "orc_spmv_dot_s"):
+        getattr(L, name).restype = C.c_float
     for name in (
         "orc_gen_dirichlet2d",
         "orc_gen_lap3d7_d",
@@ -80,7 +82,20 @@ def _is_c(a) -> bool:
 
 
 def _sfx(dtype) -> str:
-    return "z" if np.dtype(dtype).kind == "c" else "d"
+    """d / z (f64, Complex64) and s / c (f32, Complex32 -- SURVEY.md section 8f rank 2; the GPU
+    library does not implement them yet, the oracle already restates them)."""
+    dt = np.dtype(dtype)
+    if dt.kind == "c":
+        return "c" if dt.itemsize == 8 else "z"
+    return "s" if dt.itemsize == 4 else "d"
+
+
+def _is_single(dtype) -> bool:
+    return _sfx(dtype) in ("s", "c")
+
+
+def _real_dtype(dtype):
+    return np.float32 if _is_single(dtype) else np.float64
 
 
 @dataclass
@@ -97,7 +112,11 @@ class Csr:
     def __post_init__(self):
         self.indptr = np.ascontiguousarray(self.indptr, dtype=np.int64)
         self.indices = np.ascontiguousarray(self.indices, dtype=np.int32)
-        dt = np.complex128 if _is_c(self.data) else np.float64
+        d = np.asarray(self.data)
+        if d.dtype in (np.float32, np.complex64):  # f32 / Complex32 are kept (oracle only)
+            dt = d.dtype
+        else:
+            dt = np.complex128 if _is_c(self.data) else np.float64
         self.data = np.ascontiguousarray(self.data, dtype=dt)
         if self.ncols is None:
             self.ncols = self.n
@@ -159,10 +178,16 @@ def spmv_csc(nrows, ncols, indptr, indices, data, x) -> np.ndarray:
 def spmv_dot(A: Csr, x: np.ndarray):
     x = np.ascontiguousarray(x, dtype=A.dtype)
     y = np.empty(A.n, dtype=A.dtype)
-    out = np.zeros(2, dtype=np.float64)
-    getattr(lib(), f"orc_spmv_dot_{_sfx(A.dtype)}")(
+    sfx = _sfx(A.dtype)
+    if sfx == "s":
+        r = lib().orc_spmv_dot_s(_i64(A.n), _ptr(A.indptr), _ptr(A.indices), _ptr(A.data), _ptr(x), _ptr(y))
+        return y, np.float32(r)
+    out = np.zeros(2, dtype=_real_dtype(A.dtype))
+    getattr(lib(), f"orc_spmv_dot_{sfx}")(
         _i64(A.n), _ptr(A.indptr), _ptr(A.indices), _ptr(A.data), _ptr(x), _ptr(y), _ptr(out)
     )
+    if sfx == "c":
+        return y, np.complex64(complex(out[0], out[1]))
     return y, (complex(out[0], out[1]) if _is_c(A.data) else float(out[0]))
 
 
@@ -176,9 +201,19 @@ def norm2(x) -> float:
     return float(getattr(lib(), f"orc_norm2_{_sfx(x.dtype)}")(_i64(x.size), _ptr(x)))
 
 
+def _c2f(a: complex) -> np.ndarray:
+    return np.array([complex(a).real, complex(a).imag], dtype=np.float32)
+
+
 def dot(x, y):
     x = np.ascontiguousarray(x)
     y = np.ascontiguousarray(y, dtype=x.dtype)
+    if _sfx(x.dtype) == "s":
+        return np.float32(lib().orc_dot_s(_i64(x.size), _ptr(x), _ptr(y)))
+    if _sfx(x.dtype) == "c":
+        out = np.zeros(2, np.float32)
+        lib().orc_dot_c(_i64(x.size), _ptr(x), _ptr(y), _ptr(out))
+        return np.complex64(complex(out[0], out[1]))
     if _is_c(x):
         out = np.zeros(2)
         lib().orc_dot_z(_i64(x.size), _ptr(x), _ptr(y), _ptr(out))
@@ -189,6 +224,12 @@ def dot(x, y):
 def conj_dot(x, y):
     x = np.ascontiguousarray(x)
     y = np.ascontiguousarray(y, dtype=x.dtype)
+    if _sfx(x.dtype) == "s":
+        return np.float32(lib().orc_conj_dot_s(_i64(x.size), _ptr(x), _ptr(y)))
+    if _sfx(x.dtype) == "c":
+        out = np.zeros(2, np.float32)
+        lib().orc_conj_dot_c(_i64(x.size), _ptr(x), _ptr(y), _ptr(out))
+        return np.complex64(complex(out[0], out[1]))
     if _is_c(x):
         out = np.zeros(2)
         lib().orc_conj_dot_z(_i64(x.size), _ptr(x), _ptr(y), _ptr(out))
@@ -200,7 +241,11 @@ def axpy(a, x, y) -> None:
     """y += a*x in place (vecalg.rs:571-575)."""
     assert y.flags.c_contiguous
     x = np.ascontiguousarray(x, dtype=y.dtype)
-    if _is_c(y):
+    if _sfx(y.dtype) == "s":
+        lib().orc_axpy_s(_i64(y.size), C.c_float(a), _ptr(x), _ptr(y))
+    elif _sfx(y.dtype) == "c":
+        lib().orc_axpy_c(_i64(y.size), _ptr(_c2f(a)), _ptr(x), _ptr(y))
+    elif _is_c(y):
         lib().orc_axpy_z(_i64(y.size), _ptr(_c2(a)), _ptr(x), _ptr(y))
     else:
         lib().orc_axpy_d(_i64(y.size), _dbl(a), _ptr(x), _ptr(y))
@@ -210,7 +255,11 @@ def axpby(a, x, b, y) -> None:
     """y = a*x + b*y in place (vecalg.rs:586-590)."""
     assert y.flags.c_contiguous
     x = np.ascontiguousarray(x, dtype=y.dtype)
-    if _is_c(y):
+    if _sfx(y.dtype) == "s":
+        lib().orc_axpby_s(_i64(y.size), C.c_float(a), _ptr(x), C.c_float(b), _ptr(y))
+    elif _sfx(y.dtype) == "c":
+        lib().orc_axpby_c(_i64(y.size), _ptr(_c2f(a)), _ptr(x), _ptr(_c2f(b)), _ptr(y))
+    elif _is_c(y):
         lib().orc_axpby_z(_i64(y.size), _ptr(_c2(a)), _ptr(x), _ptr(_c2(b)), _ptr(y))
     else:
         lib().orc_axpby_d(_i64(y.size), _dbl(a), _ptr(x), _dbl(b), _ptr(y))
@@ -218,7 +267,11 @@ def axpby(a, x, b, y) -> None:
 
 def scale(a, x) -> None:
     assert x.flags.c_contiguous
-    if _is_c(x):
+    if _sfx(x.dtype) == "s":
+        lib().orc_scale_s(_i64(x.size), C.c_float(a), _ptr(x))
+    elif _sfx(x.dtype) == "c":
+        lib().orc_scale_c(_i64(x.size), _ptr(_c2f(a)), _ptr(x))
+    elif _is_c(x):
         lib().orc_scale_z(_i64(x.size), _ptr(_c2(a)), _ptr(x))
     else:
         lib().orc_scale_d(_i64(x.size), _dbl(a), _ptr(x))
@@ -226,7 +279,9 @@ def scale(a, x) -> None:
 
 def rscale(a: float, x) -> None:
     assert x.flags.c_contiguous
-    if _is_c(x):
+    if _is_single(x.dtype):
+        getattr(lib(), f"orc_rscale_{_sfx(x.dtype)}")(_i64(x.size), C.c_float(a), _ptr(x))
+    elif _is_c(x):
         lib().orc_rscale_z(_i64(x.size), _dbl(a), _ptr(x))
     else:
         lib().orc_scale_d(_i64(x.size), _dbl(a), _ptr(x))
@@ -237,7 +292,7 @@ def conj(x) -> np.ndarray:
     if not _is_c(x):
         return x.copy()
     out = np.empty_like(x)
-    lib().orc_conj_z(_i64(x.size), _ptr(x), _ptr(out))
+    getattr(lib(), f"orc_conj_{_sfx(x.dtype)}")(_i64(x.size), _ptr(x), _ptr(out))
     return out
 
 
@@ -247,6 +302,14 @@ def diag_apply(diag, v) -> np.ndarray:
     v = np.ascontiguousarray(v)
     diag = np.ascontiguousarray(diag)
     out = np.empty_like(v)
+    if _is_single(v.dtype):
+        if _is_c(v) and not _is_c(diag):
+            lib().orc_diag_apply_cs(_i64(v.size), _ptr(diag.astype(np.float32)), _ptr(v), _ptr(out))
+        elif _is_c(v):
+            lib().orc_diag_apply_c(_i64(v.size), _ptr(diag.astype(np.complex64)), _ptr(v), _ptr(out))
+        else:
+            lib().orc_diag_apply_s(_i64(v.size), _ptr(diag.astype(np.float32)), _ptr(v), _ptr(out))
+        return out
     if _is_c(v) and not _is_c(diag):
         lib().orc_diag_apply_zd(_i64(v.size), _ptr(diag.astype(np.float64)), _ptr(v), _ptr(out))
     elif _is_c(v):
@@ -285,7 +348,7 @@ def _pc_args(A: Csr, pc):
     if kind == "diag":
         d = np.ascontiguousarray(pc[1])
         if _is_c(A.data) and not _is_c(d):
-            return PC_DIAG_REAL, d.astype(np.float64)
+            return PC_DIAG_REAL, d.astype(_real_dtype(A.dtype))
         return PC_DIAG, d.astype(A.dtype)
     if kind == "gs_fwd":
         return PC_GS_FWD, None

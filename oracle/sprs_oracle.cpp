@@ -25,6 +25,30 @@ int g_mode = 0;
 struct cplx {
   double re, im;
 };
+// f32 / Complex32 (cauchy::Scalar is implemented for all four types; MKL dispatches s/d/c/z,
+// src/mkl_mat.rs:68-71).  T::Real is f32 there: every real-valued quantity of the f32 solvers
+// (norms, Givens scalars, tolerances, epsilon) is computed in float below.
+struct cplxf {
+  float re, im;
+};
+template <typename T>
+struct RealOf {
+  using type = double;
+};
+template <>
+struct RealOf<float> {
+  using type = float;
+};
+template <>
+struct RealOf<cplxf> {
+  using type = float;
+};
+template <typename T>
+using real_t = typename RealOf<T>::type;
+template <typename T>
+inline real_t<T> eps_of() {  // T::Real::epsilon()
+  return std::numeric_limits<real_t<T>>::epsilon();
+}
 
 // ---------- scalar traits -------------------------------------------------------------------
 inline double zero_of(double) { return 0.0; }
@@ -67,7 +91,43 @@ inline double im_of(cplx a) { return a.im; }
 // T * V with V real while T complex (DiagPrecond<Complex64,f64>, precond.rs:50)
 inline cplx mul(cplx a, double r) { return cplx{a.re * r, a.im * r}; }
 
-const double EPS = std::numeric_limits<double>::epsilon();
+
+inline float zero_of(float) { return 0.0f; }
+inline cplxf zero_of(cplxf) { return cplxf{0.0f, 0.0f}; }
+inline float one_of(float) { return 1.0f; }
+inline cplxf one_of(cplxf) { return cplxf{1.0f, 0.0f}; }
+inline float from_real(float, float r) { return r; }
+inline cplxf from_real(cplxf, float r) { return cplxf{r, 0.0f}; }
+inline float add(float a, float b) { return a + b; }
+inline float sub(float a, float b) { return a - b; }
+inline float mul(float a, float b) { return a * b; }
+inline float divi(float a, float b) { return a / b; }
+inline float neg(float a) { return -a; }
+inline float conj_of(float a) { return a; }
+inline float mul_real(float a, float r) { return a * r; }
+inline float square(float a) { return a * a; }
+inline float abs_of(float a) { return std::fabs(a); }
+inline float re_of(float a) { return a; }
+inline float im_of(float) { return 0.0f; }
+inline cplxf add(cplxf a, cplxf b) { return cplxf{a.re + b.re, a.im + b.im}; }
+inline cplxf sub(cplxf a, cplxf b) { return cplxf{a.re - b.re, a.im - b.im}; }
+inline cplxf mul(cplxf a, cplxf b) {
+  return cplxf{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+inline cplxf divi(cplxf a, cplxf b) {
+  float ns = b.re * b.re + b.im * b.im;
+  float re = a.re * b.re + a.im * b.im;
+  float im = a.im * b.re - a.re * b.im;
+  return cplxf{re / ns, im / ns};
+}
+inline cplxf neg(cplxf a) { return cplxf{-a.re, -a.im}; }
+inline cplxf conj_of(cplxf a) { return cplxf{a.re, -a.im}; }
+inline cplxf mul_real(cplxf a, float r) { return cplxf{a.re * r, a.im * r}; }
+inline float square(cplxf a) { return a.re * a.re + a.im * a.im; }
+inline float abs_of(cplxf a) { return std::hypot(a.re, a.im); }
+inline float re_of(cplxf a) { return a.re; }
+inline float im_of(cplxf a) { return a.im; }
+inline cplxf mul(cplxf a, float r) { return cplxf{a.re * r, a.im * r}; }
 
 // ---------- SpMV: src/mat.rs:68-129 ---------------------------------------------------------
 template <typename T>
@@ -124,6 +184,22 @@ inline cplx conj_dot_omp(int64_t n, const cplx* x, const cplx* y) {
   }
   return cplx{sr, si};
 }
+inline float conj_dot_omp(int64_t n, const float* x, const float* y) {
+  float s = 0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+  for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
+  return s;
+}
+inline cplxf conj_dot_omp(int64_t n, const cplxf* x, const cplxf* y) {
+  float sr = 0, si = 0;
+#pragma omp parallel for reduction(+ : sr, si) schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    cplxf t = mul(conj_of(x[i]), y[i]);
+    sr += t.re;
+    si += t.im;
+  }
+  return cplxf{sr, si};
+}
 template <typename T>
 T conj_dot(int64_t n, const T* x, const T* y) {  // vecalg.rs:564-568
   if (g_mode >= 2) return conj_dot_omp(n, x, y);
@@ -132,8 +208,8 @@ T conj_dot(int64_t n, const T* x, const T* y) {  // vecalg.rs:564-568
   return acc;
 }
 template <typename T>
-double norm2(int64_t n, const T* x) {  // vecalg.rs:601-605
-  double acc = 0.0;
+real_t<T> norm2(int64_t n, const T* x) {  // vecalg.rs:601-605 (the sum and the sqrt are T::Real)
+  real_t<T> acc = 0;
   if (g_mode >= 2) {
 #pragma omp parallel for reduction(+ : acc) schedule(static)
     for (int64_t i = 0; i < n; ++i) acc += square(x[i]);
@@ -157,7 +233,7 @@ void scale(int64_t n, T a, T* x) {  // vecalg.rs:593-595: *v *= a
   for (int64_t i = 0; i < n; ++i) x[i] = mul(x[i], a);
 }
 template <typename T>
-void rscale(int64_t n, double a, T* x) {  // vecalg.rs:597-599: *v = v.mul_real(a)
+void rscale(int64_t n, real_t<T> a, T* x) {  // vecalg.rs:597-599: *v = v.mul_real(a)
 #pragma omp parallel for schedule(static) if (g_mode >= 2)
   for (int64_t i = 0; i < n; ++i) x[i] = mul_real(x[i], a);
 }
@@ -215,7 +291,7 @@ int64_t gs_diagonals(const Csr<T>& A, T* diag) {
         found = true;
       }
     if (!found) return row;               // :72-74
-    if (square(d) < EPS) return row;      // :76-78
+    if (square(d) < eps_of<T>()) return row;      // :76-78
     diag[row] = d;
   }
   return -1;
@@ -227,7 +303,7 @@ struct Precond {
   int64_t n;
   const Csr<T>* A;     // GS kinds
   T* dinv_t;           // ORC_PC_DIAG: reciprocal (T)
-  double* dinv_r;      // ORC_PC_DIAG_REAL: reciprocal (real)
+  real_t<T>* dinv_r;   // ORC_PC_DIAG_REAL: reciprocal (real)
   T* gs_diag;          // GS kinds: cached diagonal
   T* gs_tmp;           // GS_SYM: forward result
   // precond.rs:48-52: *r = (*v) * (*s)
@@ -258,7 +334,7 @@ struct Precond {
 template <typename T>
 struct PrecondOwner {
   Precond<T> p;
-  PrecondOwner(int kind, int64_t n, const Csr<T>* A, const double* data) {
+  PrecondOwner(int kind, int64_t n, const Csr<T>* A, const void* data) {
     p.kind = kind;
     p.n = n;
     p.A = A;
@@ -274,8 +350,9 @@ struct PrecondOwner {
       const T* d = reinterpret_cast<const T*>(data);
       for (int64_t i = 0; i < n; ++i) p.dinv_t[i] = divi(one_of(T()), d[i]);
     } else if (kind == ORC_PC_DIAG_REAL) {
-      p.dinv_r = new double[n];
-      for (int64_t i = 0; i < n; ++i) p.dinv_r[i] = 1.0 / data[i];
+      p.dinv_r = new real_t<T>[n];
+      const real_t<T>* d = reinterpret_cast<const real_t<T>*>(data);
+      for (int64_t i = 0; i < n; ++i) p.dinv_r[i] = real_t<T>(1) / d[i];
     } else if (kind == ORC_PC_GS_FWD || kind == ORC_PC_GS_SYM) {
       p.gs_diag = new T[n];
       bad_row = gs_diagonals(*A, p.gs_diag);
@@ -309,17 +386,20 @@ template <typename T>
 int bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Precond<T>* M,
              const T* rhs, T* x, int64_t max_iter, double tol, T* ws, int64_t* iters,
              double* resid, Hist& h) {
+  using R = real_t<T>;
+  const R EPS_T = eps_of<T>();
+  const R tol_r = (R)tol;
   const int64_t n = n_rhs;
   if (n != size) return ORC_INCOMPATIBLE_FORMAT;  // :44 / :214
   if (n != n_x) return ORC_INCOMPATIBLE_FORMAT;   // :49 / :219
-  const double rhs_norm = norm2(n, rhs);          // :55 / :225
-  if (rhs_norm <= EPS) {                          // :56-60
+  const R rhs_norm = norm2(n, rhs);          // :55 / :225
+  if (rhs_norm <= EPS_T) {                          // :56-60
     zero_vec(n, x);
     *iters = 0;
     *resid = rhs_norm;
     return ORC_OK;
   }
-  const double tol2 = tol * rhs_norm;  // :61
+  const R tol2 = tol_r * rhs_norm;  // :61
   T *r, *r0, *y, *p, *v, *t, *z;
   if (M) {  // :235-241
     r = ws, r0 = ws + n, y = ws + 2 * n, p = ws + 3 * n, v = ws + 4 * n, t = ws + 5 * n,
@@ -332,14 +412,14 @@ int bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Pr
   A.mul_vec(x, r);                       // :73 / :244
   axpy(n, neg(one_of(T())), rhs, r);     // :75 r = A*x - rhs
   copy_vec(n, r, r0);                    // :78
-  const double r0_norm = norm2(n, r0);   // :80
+  const R r0_norm = norm2(n, r0);   // :80
   h.put(0, r0_norm / rhs_norm);
   if (r0_norm <= tol2) {                 // :81-83
     *iters = 0;
     *resid = r0_norm / rhs_norm;
     return ORC_OK;
   }
-  double r0_norm_tol = r0_norm * EPS;    // :84-85
+  R r0_norm_tol = r0_norm * EPS_T;    // :84-85
   r0_norm_tol = r0_norm_tol * r0_norm_tol;
 
   T rho = from_real(T(), r0_norm * r0_norm);  // :88
@@ -355,13 +435,13 @@ int bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Pr
   if (M) M->apply(r, z);                             // :273
   A.mul_vec(z, t);                                   // :104 / :275
   T tmp = conj_dot(n, t, t);                         // :107 / :278
-  T w = re_of(tmp) > 0.0 ? divi(conj_dot(n, t, r), tmp) : zero_of(T());  // :108-113
+  T w = re_of(tmp) > 0 ? divi(conj_dot(n, t, r), tmp) : zero_of(T());  // :108-113
   axpy(n, neg(alpha), y, x);                         // :115 / :288
   axpy(n, neg(w), z, x);                             // :117 / :290
   axpy(n, neg(w), t, r);                             // :120 / :293
 
   for (int64_t its = 1; its < max_iter; ++its) {     // :122 / :295
-    const double r_norm = norm2(n, r);               // :123
+    const R r_norm = norm2(n, r);               // :123
     h.put(its, r_norm / rhs_norm);
     if (r_norm <= tol2) {                            // :124-126
       *iters = its;
@@ -374,9 +454,9 @@ int bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Pr
       A.mul_vec(x, r);
       axpy(n, neg(one_of(T())), rhs, r);
       copy_vec(n, r, r0);
-      const double rn = norm2(n, r);
+      const R rn = norm2(n, r);
       rho = from_real(T(), rn * rn);
-      r0_norm_tol = re_of(rho) * EPS * EPS;
+      r0_norm_tol = re_of(rho) * EPS_T * EPS_T;
     }
     const T beta = mul(divi(rho, rho_old), divi(alpha, w));  // :146 / :319
     axpby(n, mul(neg(beta), w), v, beta, p);                 // :155 / :324
@@ -384,7 +464,7 @@ int bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Pr
     if (M) M->apply(p, y);                                   // :328
     A.mul_vec(y, v);                                         // :160 / :329
     tmp = conj_dot(n, r0, v);                                // :163 / :332
-    if (abs_of(tmp) <= 0.0) {                                // :164-167
+    if (abs_of(tmp) <= 0) {                                // :164-167
       *iters = its;
       return ORC_BREAKDOWN;
     }
@@ -393,7 +473,7 @@ int bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Pr
     if (M) M->apply(r, z);                                   // :343
     A.mul_vec(z, t);                                         // :175 / :344
     tmp = conj_dot(n, t, t);                                 // :178
-    w = re_of(tmp) > 0.0 ? divi(conj_dot(n, t, r), tmp) : zero_of(T());  // :179-186
+    w = re_of(tmp) > 0 ? divi(conj_dot(n, t, r), tmp) : zero_of(T());  // :179-186
     axpy(n, neg(alpha), y, x);                               // :188 / :355
     axpy(n, neg(w), z, x);                                   // :191 / :357
     axpy(n, neg(w), t, r);                                   // :196 / :362
@@ -408,19 +488,22 @@ template <typename T>
 int minres(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Precond<T>* M,
            bool cs, const T* rhs, T* x, int64_t max_iter, double tol, T* ws, int64_t* iters,
            double* resid, Hist& h) {
+  using R = real_t<T>;
+  const R EPS_T = eps_of<T>();
+  const R tol_r = (R)tol;
   const int64_t n = n_rhs;
   if (n != size) return ORC_INCOMPATIBLE_FORMAT;
   if (n != n_x) return ORC_INCOMPATIBLE_FORMAT;
-  const double rhs_norm = norm2(n, rhs);  // :51
-  if (rhs_norm <= EPS) {
+  const R rhs_norm = norm2(n, rhs);  // :51
+  if (rhs_norm <= EPS_T) {
     zero_vec(n, x);
     *iters = 0;
     *resid = rhs_norm;
     return ORC_OK;
   }
-  const double threshold = tol * rhs_norm;  // :57
+  const R threshold = tol_r * rhs_norm;  // :57
   T c = one_of(T()), c_old = one_of(T());   // :60-64
-  double s = 0.0, s_old = 0.0;
+  R s = 0.0, s_old = 0;
   T eta = one_of(T());
   T* v_old = ws;            // :68-73 / :216-223 / cs_minres.rs:66-72
   T* v_new = ws + n;
@@ -435,28 +518,28 @@ int minres(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Prec
   copy_vec(n, rhs, v_new);                   // :77
   A.mul_vec(x, v_old);                       // :78
   axpy(n, neg(one_of(T())), v_old, v_new);   // :80 v_new = rhs - A*x
-  double res_norm = norm2(n, v_new);         // :81 / :231
-  double beta_new, beta_one;
+  R res_norm = norm2(n, v_new);         // :81 / :231
+  R beta_new, beta_one;
   if (M) {
     M->apply(v_new, w_new);                  // :233
     T b2 = conj_dot(n, v_new, w_new);        // :235
-    if (re_of(b2) < EPS || im_of(b2) > EPS * re_of(b2)) return ORC_INVALID_PRECOND;  // :236-244
+    if (re_of(b2) < EPS_T || im_of(b2) > EPS_T * re_of(b2)) return ORC_INVALID_PRECOND;  // :236-244
     beta_new = std::sqrt(re_of(b2));         // :245
     beta_one = beta_new;
-    const double ts = 1.0 / beta_new;        // :248-250
+    const R ts = R(1) / beta_new;        // :248-250
     rscale(n, ts, v_new);
     rscale(n, ts, w_new);
   } else {
     beta_new = res_norm;                     // :82-84
     beta_one = beta_new;
-    rscale(n, 1.0 / beta_new, v_new);
+    rscale(n, R(1) / beta_new, v_new);
   }
   zero_vec(n, v);      // :86-88
   zero_vec(n, p_old);
   zero_vec(n, p);
 
   for (int64_t its = 0; its < max_iter; ++its) {  // :90
-    const double beta = beta_new;
+    const R beta = beta_new;
     T* v_t = v_old;  // :92-96 pointer rotation
     v_old = v;
     v = v_new;
@@ -485,25 +568,25 @@ int minres(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Prec
     if (M) {
       M->apply(v_new, w_new);                      // :276
       T b2 = conj_dot(n, v_new, w_new);            // :278
-      if (re_of(b2) < EPS || im_of(b2) > EPS * re_of(b2)) {  // :279-287
+      if (re_of(b2) < EPS_T || im_of(b2) > EPS_T * re_of(b2)) {  // :279-287
         *iters = its;
         return ORC_INVALID_PRECOND;
       }
       beta_new = std::sqrt(re_of(b2));             // :288
-      const double ts = 1.0 / beta_new;            // :289-291
+      const R ts = R(1) / beta_new;            // :289-291
       rscale(n, ts, v_new);
       rscale(n, ts, w_new);
     } else {
       beta_new = norm2(n, v_new);                  // :120 / cs:106
-      rscale(n, 1.0 / beta_new, v_new);            // :121 / cs:107
+      rscale(n, R(1) / beta_new, v_new);            // :121 / cs:107
     }
     // Givens rotation: minres.rs:132-148 ; cs_minres.rs:119-134 (conjugations differ)
-    const double r3 = s_old * beta;
+    const R r3 = s_old * beta;
     const T tr = cs ? mul_real(conj_of(c_old), beta) : mul_real(c_old, beta);
     const T r2 = add(mul_real(alpha, s), mul(c, tr));
     const T r1_hat = cs ? sub(mul(conj_of(c), alpha), mul_real(tr, s))
                         : sub(mul(c, alpha), mul_real(tr, s));
-    const double r1_inv = 1.0 / std::sqrt(square(r1_hat) + beta_new * beta_new);
+    const R r1_inv = R(1) / std::sqrt(square(r1_hat) + beta_new * beta_new);
     c_old = c;
     s_old = s;
     c = cs ? mul_real(conj_of(r1_hat), r1_inv) : mul_real(r1_hat, r1_inv);
@@ -536,6 +619,8 @@ template <typename T>
 int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x,
                  const Csr<T>& A, const T* rhs, T* x, int64_t max_iter, double eps, T* ws,
                  int64_t* iters, double* resid, Hist& h) {
+  using R = real_t<T>;
+  const R EPS_T = eps_of<T>();
   if (nrows != ncols) return ORC_INCOMPATIBLE_FORMAT;  // :16-20 (GaussSeidel::new)
   if (!is_csr) return ORC_INCOMPATIBLE_FORMAT;         // :22-26
   if (n_rhs != nrows) return ORC_INCOMPATIBLE_FORMAT;  // :41-45
@@ -545,7 +630,7 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
     return ORC_INSUFFICIENT_ITER;
   }
   const int64_t n = n_rhs;
-  double b_norm = 0.0;
+  R b_norm = 0;
   T* res = ws;       // workspace[0..n]
   T* diag = ws + n;  // workspace[n..2n]
   for (int64_t row = 0; row < n; ++row) {  // :60-86 unrolled first sweep
@@ -561,7 +646,7 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
         found = true;
       }
     }
-    if (!found || square(d) < EPS) {  // :72-78
+    if (!found || square(d) < EPS_T) {  // :72-78
       *iters = row;
       return ORC_ZERO_DIAGONAL;
     }
@@ -569,10 +654,10 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
     b_norm += square(rhs[row]);                 // :83
     x[row] = divi(sub(rhs[row], sigma), d);     // :84
   }
-  const double tol2 = eps * std::sqrt(b_norm);  // :87
+  const R tol2 = (R)eps * std::sqrt(b_norm);  // :87
   A.mul_vec(x, res);                            // :90
   axpy(n, neg(one_of(T())), rhs, res);          // :97
-  double rn = norm2(n, res);                    // :104
+  R rn = norm2(n, res);                    // :104
   h.put(0, rn);
   if (rn <= tol2) {                             // :106-108
     *iters = 1;
@@ -597,8 +682,8 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
 
 template <typename T>
 int run_bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr,
-                 const int32_t* idx, const double* a, int pc_kind, const double* pc_data,
-                 const double* rhs, double* x, int64_t max_iter, double tol, double* work,
+                 const int32_t* idx, const void* a, int pc_kind, const void* pc_data,
+                 const void* rhs, void* x, int64_t max_iter, double tol, void* work,
                  int64_t* iters, double* resid, double* hist, int64_t hist_cap,
                  int64_t* hist_len) {
   Csr<T> A{size, indptr, idx, reinterpret_cast<const T*>(a)};
@@ -626,8 +711,8 @@ int run_bicgstab(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr
 
 template <typename T>
 int run_minres(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr, const int32_t* idx,
-               const double* a, int pc_kind, const double* pc_data, bool cs, const double* rhs,
-               double* x, int64_t max_iter, double tol, double* work, int64_t* iters,
+               const void* a, int pc_kind, const void* pc_data, bool cs, const void* rhs,
+               void* x, int64_t max_iter, double tol, void* work, int64_t* iters,
                double* resid, double* hist, int64_t hist_cap, int64_t* hist_len) {
   Csr<T> A{size, indptr, idx, reinterpret_cast<const T*>(a)};
   Hist h{hist, hist_cap, 0};
@@ -654,8 +739,8 @@ int run_minres(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr, 
 
 template <typename T>
 int run_gs(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x,
-           const int64_t* indptr, const int32_t* idx, const double* a, const double* rhs,
-           double* x, int64_t max_iter, double eps, double* work, int64_t* iters, double* resid,
+           const int64_t* indptr, const int32_t* idx, const void* a, const void* rhs,
+           void* x, int64_t max_iter, double eps, void* work, int64_t* iters, double* resid,
            double* hist, int64_t hist_cap, int64_t* hist_len) {
   Csr<T> A{nrows, indptr, idx, reinterpret_cast<const T*>(a)};
   Hist h{hist, hist_cap, 0};
@@ -669,8 +754,8 @@ int run_gs(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x,
 }
 
 template <typename T>
-int run_gs_apply(int64_t n, const int64_t* indptr, const int32_t* idx, const double* a,
-                 int symmetric, const double* in, double* out) {
+int run_gs_apply(int64_t n, const int64_t* indptr, const int32_t* idx, const void* a,
+                 int symmetric, const void* in, void* out) {
   Csr<T> A{n, indptr, idx, reinterpret_cast<const T*>(a)};
   PrecondOwner<T> po(symmetric ? ORC_PC_GS_SYM : ORC_PC_GS_FWD, n, &A, nullptr);
   if (!po.ok) return ORC_ZERO_DIAGONAL;
@@ -915,6 +1000,108 @@ int orc_gauss_seidel_z(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, 
                        int64_t* hist_len) {
   return run_gs<cplx>(nrows, ncols, is_csr, n_rhs, n_x, indptr, idx, a, rhs, x, max_iter, eps,
                       work, iters, resid, hist, hist_cap, hist_len);
+}
+
+// ---------- f32 / Complex32 entry points (float arrays, interleaved re,im for _c) -------------
+#define SOLVER_ARGS_F                                                                            \
+  int64_t size, int64_t n_rhs, int64_t n_x, const int64_t *indptr, const int32_t *idx,          \
+      const float *a, int pc_kind, const float *pc_data, const float *rhs, float *x,            \
+      int64_t max_iter, double tol, float *work, int64_t *iters, double *resid, double *hist,   \
+      int64_t hist_cap, int64_t *hist_len
+void orc_spmv_s(int64_t n, const int64_t* ip, const int32_t* idx, const float* a, const float* x, float* y) {
+  spmv_serial<float>(n, ip, idx, a, x, y);
+}
+void orc_spmv_c(int64_t n, const int64_t* ip, const int32_t* idx, const float* a, const float* x, float* y) {
+  spmv_serial<cplxf>(n, ip, idx, (const cplxf*)a, (const cplxf*)x, (cplxf*)y);
+}
+float orc_spmv_dot_s(int64_t n, const int64_t* ip, const int32_t* idx, const float* a, const float* x, float* y) {
+  Csr<float> A{n, ip, idx, a};
+  int m = g_mode;
+  g_mode = 0;
+  const float r = A.mul_vec_dot(x, y);
+  g_mode = m;
+  return r;
+}
+void orc_spmv_dot_c(int64_t n, const int64_t* ip, const int32_t* idx, const float* a, const float* x, float* y, float* out) {
+  Csr<cplxf> A{n, ip, idx, (const cplxf*)a};
+  int m = g_mode;
+  g_mode = 0;
+  const cplxf r = A.mul_vec_dot((const cplxf*)x, (cplxf*)y);
+  g_mode = m;
+  out[0] = r.re;
+  out[1] = r.im;
+}
+float orc_norm2_s(int64_t n, const float* x) { return norm2<float>(n, x); }
+float orc_norm2_c(int64_t n, const float* x) { return norm2<cplxf>(n, (const cplxf*)x); }
+float orc_dot_s(int64_t n, const float* x, const float* y) { return dot_fb<float>(n, x, y); }
+void orc_scale_s(int64_t n, float a, float* x) { scale<float>(n, a, x); }
+void orc_scale_c(int64_t n, const float* a, float* x) { scale<cplxf>(n, cplxf{a[0], a[1]}, (cplxf*)x); }
+void orc_rscale_s(int64_t n, float a, float* x) { rscale<float>(n, a, x); }
+void orc_rscale_c(int64_t n, float a, float* x) { rscale<cplxf>(n, a, (cplxf*)x); }
+void orc_axpy_c(int64_t n, const float* a, const float* x, float* y) {
+  axpy<cplxf>(n, cplxf{a[0], a[1]}, (const cplxf*)x, (cplxf*)y);
+}
+void orc_axpby_c(int64_t n, const float* a, const float* x, const float* b, float* y) {
+  axpby<cplxf>(n, cplxf{a[0], a[1]}, (const cplxf*)x, cplxf{b[0], b[1]}, (cplxf*)y);
+}
+void orc_conj_c(int64_t n, const float* x, float* out) { conj_vec<cplxf>(n, (const cplxf*)x, (cplxf*)out); }
+void orc_diag_apply_s(int64_t n, const float* diag, const float* in, float* out) {
+  PrecondOwner<float> po(ORC_PC_DIAG, n, nullptr, diag);
+  po.p.apply(in, out);
+}
+void orc_diag_apply_c(int64_t n, const float* diag, const float* in, float* out) {
+  PrecondOwner<cplxf> po(ORC_PC_DIAG, n, nullptr, diag);
+  po.p.apply((const cplxf*)in, (cplxf*)out);
+}
+void orc_diag_apply_cs(int64_t n, const float* diag, const float* in, float* out) {  // DiagPrecond<Complex32, f32>
+  PrecondOwner<cplxf> po(ORC_PC_DIAG_REAL, n, nullptr, diag);
+  po.p.apply((const cplxf*)in, (cplxf*)out);
+}
+int orc_gs_apply_s(int64_t n, const int64_t* ip, const int32_t* idx, const float* a, int sym, const float* in, float* out) {
+  return run_gs_apply<float>(n, ip, idx, a, sym, in, out);
+}
+int orc_gs_apply_c(int64_t n, const int64_t* ip, const int32_t* idx, const float* a, int sym, const float* in, float* out) {
+  return run_gs_apply<cplxf>(n, ip, idx, a, sym, in, out);
+}
+int orc_bicgstab_s(SOLVER_ARGS_F) {
+  return run_bicgstab<float>(size, n_rhs, n_x, indptr, idx, a, pc_kind, pc_data, rhs, x, max_iter, tol, work, iters, resid,
+                             hist, hist_cap, hist_len);
+}
+int orc_bicgstab_c(SOLVER_ARGS_F) {
+  return run_bicgstab<cplxf>(size, n_rhs, n_x, indptr, idx, a, pc_kind, pc_data, rhs, x, max_iter, tol, work, iters, resid,
+                             hist, hist_cap, hist_len);
+}
+int orc_minres_s(SOLVER_ARGS_F) {
+  return run_minres<float>(size, n_rhs, n_x, indptr, idx, a, pc_kind, pc_data, false, rhs, x, max_iter, tol, work, iters,
+                           resid, hist, hist_cap, hist_len);
+}
+int orc_minres_c(SOLVER_ARGS_F) {
+  return run_minres<cplxf>(size, n_rhs, n_x, indptr, idx, a, pc_kind, pc_data, false, rhs, x, max_iter, tol, work, iters,
+                           resid, hist, hist_cap, hist_len);
+}
+int orc_csminres_s(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr, const int32_t* idx, const float* a,
+                   const float* rhs, float* x, int64_t max_iter, double tol, float* work, int64_t* iters, double* resid,
+                   double* hist, int64_t hist_cap, int64_t* hist_len) {
+  return run_minres<float>(size, n_rhs, n_x, indptr, idx, a, ORC_PC_NONE, nullptr, true, rhs, x, max_iter, tol, work, iters,
+                           resid, hist, hist_cap, hist_len);
+}
+int orc_csminres_c(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr, const int32_t* idx, const float* a,
+                   const float* rhs, float* x, int64_t max_iter, double tol, float* work, int64_t* iters, double* resid,
+                   double* hist, int64_t hist_cap, int64_t* hist_len) {
+  return run_minres<cplxf>(size, n_rhs, n_x, indptr, idx, a, ORC_PC_NONE, nullptr, true, rhs, x, max_iter, tol, work, iters,
+                           resid, hist, hist_cap, hist_len);
+}
+int orc_gauss_seidel_s(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x, const int64_t* indptr,
+                       const int32_t* idx, const float* a, const float* rhs, float* x, int64_t max_iter, double eps,
+                       float* work, int64_t* iters, double* resid, double* hist, int64_t hist_cap, int64_t* hist_len) {
+  return run_gs<float>(nrows, ncols, is_csr, n_rhs, n_x, indptr, idx, a, rhs, x, max_iter, eps, work, iters, resid, hist,
+                       hist_cap, hist_len);
+}
+int orc_gauss_seidel_c(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x, const int64_t* indptr,
+                       const int32_t* idx, const float* a, const float* rhs, float* x, int64_t max_iter, double eps,
+                       float* work, int64_t* iters, double* resid, double* hist, int64_t hist_cap, int64_t* hist_len) {
+  return run_gs<cplxf>(nrows, ncols, is_csr, n_rhs, n_x, indptr, idx, a, rhs, x, max_iter, eps, work, iters, resid, hist,
+                       hist_cap, hist_len);
 }
 
 // ---------- generators ----------------------------------------------------------------------

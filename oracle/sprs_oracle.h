@@ -175,6 +175,51 @@ void orc_set_threads(int n);
 void orc_set_mode(int mode);
 int orc_get_mode(void);
 
+/* ---- f32 / Complex32 (float arrays, interleaved re,im for _c; all real-valued solver quantities in
+ * float, thresholds with f32::EPSILON).  Restated for SURVEY.md section 8f rank 2; pinned by the
+ * reference's f32 / c32 vecalg KATs (src/vecalg.rs:647-677, doctests :122-132), otherwise by
+ * agreement with the f64 restatement to float accuracy (tests/test_oracle_f32.py). */
+void orc_spmv_s(int64_t n, const int64_t* indptr, const int32_t* idx, const float* a, const float* x, float* y);
+void orc_spmv_c(int64_t n, const int64_t* indptr, const int32_t* idx, const float* a, const float* x, float* y);
+float orc_spmv_dot_s(int64_t n, const int64_t* indptr, const int32_t* idx, const float* a, const float* x, float* y);
+void orc_spmv_dot_c(int64_t n, const int64_t* indptr, const int32_t* idx, const float* a, const float* x, float* y, float* out);
+float orc_norm2_s(int64_t n, const float* x);
+float orc_norm2_c(int64_t n, const float* x);
+float orc_dot_s(int64_t n, const float* x, const float* y);
+void orc_scale_s(int64_t n, float a, float* x);
+void orc_scale_c(int64_t n, const float* a, float* x);
+void orc_rscale_s(int64_t n, float a, float* x);
+void orc_rscale_c(int64_t n, float a, float* x);
+void orc_axpy_c(int64_t n, const float* a, const float* x, float* y);
+void orc_axpby_c(int64_t n, const float* a, const float* x, const float* b, float* y);
+void orc_conj_c(int64_t n, const float* x, float* out);
+void orc_diag_apply_s(int64_t n, const float* diag, const float* in, float* out);
+void orc_diag_apply_c(int64_t n, const float* diag, const float* in, float* out);
+void orc_diag_apply_cs(int64_t n, const float* diag, const float* in, float* out);
+int orc_gs_apply_s(int64_t n, const int64_t* indptr, const int32_t* idx, const float* a, int symmetric, const float* in, float* out);
+int orc_gs_apply_c(int64_t n, const int64_t* indptr, const int32_t* idx, const float* a, int symmetric, const float* in, float* out);
+#define ORC_SOLVER_ARGS_F                                                                        \
+  int64_t size, int64_t n_rhs, int64_t n_x, const int64_t *indptr, const int32_t *idx,          \
+      const float *a, int pc_kind, const float *pc_data, const float *rhs, float *x,            \
+      int64_t max_iter, double tol, float *work, int64_t *iters, double *resid, double *hist,   \
+      int64_t hist_cap, int64_t *hist_len
+int orc_bicgstab_s(ORC_SOLVER_ARGS_F);
+int orc_bicgstab_c(ORC_SOLVER_ARGS_F);
+int orc_minres_s(ORC_SOLVER_ARGS_F);
+int orc_minres_c(ORC_SOLVER_ARGS_F);
+int orc_csminres_s(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr, const int32_t* idx, const float* a,
+                   const float* rhs, float* x, int64_t max_iter, double tol, float* work, int64_t* iters, double* resid,
+                   double* hist, int64_t hist_cap, int64_t* hist_len);
+int orc_csminres_c(int64_t size, int64_t n_rhs, int64_t n_x, const int64_t* indptr, const int32_t* idx, const float* a,
+                   const float* rhs, float* x, int64_t max_iter, double tol, float* work, int64_t* iters, double* resid,
+                   double* hist, int64_t hist_cap, int64_t* hist_len);
+int orc_gauss_seidel_s(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x, const int64_t* indptr,
+                       const int32_t* idx, const float* a, const float* rhs, float* x, int64_t max_iter, double eps,
+                       float* work, int64_t* iters, double* resid, double* hist, int64_t hist_cap, int64_t* hist_len);
+int orc_gauss_seidel_c(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x, const int64_t* indptr,
+                       const int32_t* idx, const float* a, const float* rhs, float* x, int64_t max_iter, double eps,
+                       float* work, int64_t* iters, double* resid, double* hist, int64_t hist_cap, int64_t* hist_len);
+
 #ifdef __cplusplus
 }
 #endif
