@@ -425,7 +425,7 @@ def _noise_floor(orc, solver, A, rhs, pc, tol, max_iter, base, k=50):
     spread = np.zeros(k)
     iters = [base.iters]
     try:
-        for nt in (2, 3, 5, 8):
+        for nt in (2, 3, 5, 8, 2, 3, 5, 8):  # twice: libgomp combines the partial sums in arrival order
             orc.set_threads(nt)
             orc.set_mode(2)
             v = _oracle(orc, solver, A, rhs, pc, tol, max_iter)
