@@ -15,11 +15,20 @@
 #include <limits>
 #include <omp.h>
 
+#include <algorithm>
+#include <vector>
+
 namespace {
 
 // 0 = serial everything (bit-defining oracle; = reference without `parallel`/`mkl`),
 // 1 = OpenMP row-parallel SpMV only (= reference `parallel` feature, rayon; same numerics),
-// 2 = OpenMP SpMV + OpenMP vector ops (stand-in for the `mkl` iomp build; summation order differs).
+// 2 = OpenMP SpMV + OpenMP vector ops (stand-in for the `mkl` iomp build; summation order differs),
+// 3 = "exact-dot" flavour: as 2, but every dot / conj_dot / norm2 (and the b-norm of GaussSeidel::solve)
+//     is the EXACT sum of the exact products, rounded once (Kulisch-style superaccumulator below).
+//     Element-wise work (SpMV folds, axpy, Jacobi, GS sweeps) is untouched.  This is the one member
+//     of the family "reference algorithm + some summation order" that does not depend on the order,
+//     so a second implementation with exactly rounded sums (the GPU library) must reproduce its
+//     residual history bit for bit over every iteration.
 int g_mode = 0;
 
 struct cplx {
@@ -161,9 +170,170 @@ void spmv(int64_t n, const int64_t* indptr, const int32_t* idx, const T* a, cons
     spmv_serial(n, indptr, idx, a, x, y);
 }
 
+// ---------- exact sums (mode 3) ---------------------------------------------------------------
+// Fixed-point accumulator over the whole double range: limb i carries the bits of weight
+// 2^(32 i - 1074).  A double m * 2^(e-1075) is split over three limbs and added without any
+// rounding; limbs are int64, so 2^30 additions fit before carries must be propagated.
+struct SuperAcc {
+  static constexpr int N = 72;
+  int64_t limb[N];
+  int64_t count;
+  bool special;  // a NaN / infinity went in
+  SuperAcc() { clear(); }
+  void clear() {
+    std::memset(limb, 0, sizeof(limb));
+    count = 0;
+    special = false;
+  }
+  void normalize() {
+    for (int i = 0; i + 1 < N; ++i) {
+      const int64_t c = limb[i] >> 32;  // floor
+      limb[i] -= c * ((int64_t)1 << 32);
+      limb[i + 1] += c;
+    }
+    count = 0;
+  }
+  inline void add(double x) {
+    uint64_t bits;
+    std::memcpy(&bits, &x, 8);
+    int e = (int)((bits >> 52) & 0x7ff);
+    uint64_t m = bits & (((uint64_t)1 << 52) - 1);
+    if (e == 0) {
+      if (m == 0) return;
+      e = 1;
+    } else if (e == 0x7ff) {
+      special = true;
+      return;
+    } else {
+      m |= (uint64_t)1 << 52;
+    }
+    const int pos = e - 1, i = pos >> 5, sh = pos & 31;
+    const unsigned __int128 v = (unsigned __int128)m << sh;
+    const int64_t a0 = (int64_t)(uint32_t)v, a1 = (int64_t)(uint32_t)(v >> 32), a2 = (int64_t)(uint64_t)(v >> 64);
+    if (bits >> 63) {
+      limb[i] -= a0;
+      limb[i + 1] -= a1;
+      limb[i + 2] -= a2;
+    } else {
+      limb[i] += a0;
+      limb[i + 1] += a1;
+      limb[i + 2] += a2;
+    }
+    if (++count >= ((int64_t)1 << 29)) normalize();
+  }
+  // += a * b exactly: p = fl(a b), e = a b - p (one fma; exact barring underflow)
+  __attribute__((target("fma"))) inline void add_prod(double a, double b) {
+    const double p = a * b;
+    const double e = __builtin_fma(a, b, -p);
+    add(p);
+    add(e);
+  }
+  void merge(const SuperAcc& o) {
+    normalize();
+    SuperAcc t = o;
+    t.normalize();
+    for (int i = 0; i < N; ++i) limb[i] += t.limb[i];
+    special = special || o.special;
+    normalize();
+  }
+  // the exact value rounded to nearest-even double
+  double round() {
+    if (special) return std::numeric_limits<double>::quiet_NaN();
+    normalize();
+    bool negative = limb[N - 1] < 0;
+    if (negative) {
+      for (int i = 0; i < N; ++i) limb[i] = -limb[i];
+      normalize();
+    }
+    int k = N - 1;
+    while (k >= 0 && limb[k] == 0) --k;
+    if (k < 0) return 0.0;
+    auto L = [&](int i) -> unsigned __int128 { return i >= 0 ? (unsigned __int128)(uint64_t)limb[i] : 0; };
+    const unsigned __int128 v = (L(k) << 64) | (L(k - 1) << 32) | L(k - 2);
+    bool sticky = false;
+    for (int i = k - 3; i >= 0 && !sticky; --i) sticky = limb[i] != 0;
+    int hb = 95;
+    while (!((v >> hb) & 1)) --hb;  // limb[k] != 0  =>  hb >= 64
+    const int shift = hb - 52;
+    uint64_t mant = (uint64_t)(v >> shift);
+    const unsigned __int128 rem = v & (((unsigned __int128)1 << shift) - 1);
+    const unsigned __int128 half = (unsigned __int128)1 << (shift - 1);
+    if (rem > half || (rem == half && (sticky || (mant & 1)))) ++mant;
+    const double r = std::ldexp((double)mant, shift + 32 * (k - 2) - 1074);
+    return negative ? -r : r;
+  }
+};
+
+// Exact sum over i of f(i) contributions, in parallel chunks (exactness makes the split irrelevant).
+template <typename F>
+double exact_sum(int64_t n, F contribute) {
+  SuperAcc total;
+#pragma omp parallel
+  {
+    SuperAcc local;
+#pragma omp for schedule(static) nowait
+    for (int64_t i = 0; i < n; ++i) contribute(local, i);
+#pragma omp critical(spb_oracle_exact_merge)
+    total.merge(local);
+  }
+  return total.round();
+}
+// products of floats are exact in double
+inline double ex(float v) { return (double)v; }
+inline double ex(double v) { return v; }
+template <typename R>
+inline void exact_prod(SuperAcc& a, R x, R y) {
+  if (sizeof(R) == 4)
+    a.add(ex(x) * ex(y));
+  else
+    a.add_prod(ex(x), ex(y));
+}
+// kind: 0 dot (no conjugate), 1 conj_dot.  Real types.
+inline double exact_dot(int64_t n, const double* x, const double* y, int) {
+  return exact_sum(n, [&](SuperAcc& a, int64_t i) { exact_prod(a, x[i], y[i]); });
+}
+inline float exact_dot(int64_t n, const float* x, const float* y, int) {
+  return (float)exact_sum(n, [&](SuperAcc& a, int64_t i) { exact_prod(a, x[i], y[i]); });
+}
+template <typename C>
+inline C exact_dot_c(int64_t n, const C* x, const C* y, int kind) {
+  using R = decltype(x->re);
+  const R sg = kind == 1 ? R(-1) : R(1);  // conj_dot: conj(x) . y
+  const double re = exact_sum(n, [&](SuperAcc& a, int64_t i) {
+    exact_prod(a, x[i].re, y[i].re);
+    exact_prod(a, (R)(-sg * x[i].im), y[i].im);
+  });
+  const double im = exact_sum(n, [&](SuperAcc& a, int64_t i) {
+    exact_prod(a, x[i].re, y[i].im);
+    exact_prod(a, (R)(sg * x[i].im), y[i].re);
+  });
+  return C{(R)re, (R)im};
+}
+inline cplx exact_dot(int64_t n, const cplx* x, const cplx* y, int kind) { return exact_dot_c(n, x, y, kind); }
+inline cplxf exact_dot(int64_t n, const cplxf* x, const cplxf* y, int kind) { return exact_dot_c(n, x, y, kind); }
+inline double exact_sumsq(int64_t n, const double* x) {
+  return exact_sum(n, [&](SuperAcc& a, int64_t i) { exact_prod(a, x[i], x[i]); });
+}
+inline float exact_sumsq(int64_t n, const float* x) {
+  return (float)exact_sum(n, [&](SuperAcc& a, int64_t i) { exact_prod(a, x[i], x[i]); });
+}
+inline double exact_sumsq(int64_t n, const cplx* x) {
+  return exact_sum(n, [&](SuperAcc& a, int64_t i) {
+    exact_prod(a, x[i].re, x[i].re);
+    exact_prod(a, x[i].im, x[i].im);
+  });
+}
+inline float exact_sumsq(int64_t n, const cplxf* x) {
+  return (float)exact_sum(n, [&](SuperAcc& a, int64_t i) {
+    exact_prod(a, x[i].re, x[i].re);
+    exact_prod(a, x[i].im, x[i].im);
+  });
+}
+
 // ---------- vecalg fallbacks: src/vecalg.rs:556-605 -----------------------------------------
 template <typename T>
 T dot_fb(int64_t n, const T* x, const T* y) {  // vecalg.rs:557-561
+  if (g_mode == 3) return exact_dot(n, x, y, 0);
   T acc = zero_of(T());
   for (int64_t i = 0; i < n; ++i) acc = add(acc, mul(x[i], y[i]));
   return acc;
@@ -202,6 +372,7 @@ inline cplxf conj_dot_omp(int64_t n, const cplxf* x, const cplxf* y) {
 }
 template <typename T>
 T conj_dot(int64_t n, const T* x, const T* y) {  // vecalg.rs:564-568
+  if (g_mode == 3) return exact_dot(n, x, y, 1);
   if (g_mode >= 2) return conj_dot_omp(n, x, y);
   T acc = zero_of(T());
   for (int64_t i = 0; i < n; ++i) acc = add(acc, mul(conj_of(x[i]), y[i]));
@@ -210,6 +381,7 @@ T conj_dot(int64_t n, const T* x, const T* y) {  // vecalg.rs:564-568
 template <typename T>
 real_t<T> norm2(int64_t n, const T* x) {  // vecalg.rs:601-605 (the sum and the sqrt are T::Real)
   real_t<T> acc = 0;
+  if (g_mode == 3) return std::sqrt(exact_sumsq(n, x));
   if (g_mode >= 2) {
 #pragma omp parallel for reduction(+ : acc) schedule(static)
     for (int64_t i = 0; i < n; ++i) acc += square(x[i]);
@@ -297,6 +469,57 @@ int64_t gs_diagonals(const Csr<T>& A, T* diag) {
   return -1;
 }
 
+// Level schedule of a triangular dependency pattern (modes >= 1 only: lets the timed CPU arm and
+// the exact-dot flavour run the Gauss-Seidel sweeps on all cores).  Rows of one level do not
+// depend on each other; every row still folds its own sigma in CSR order from the same operand
+// values as the sequential sweep, so the result is bit-identical to it (tests/test_oracle_exact.py).
+struct Levels {
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> rows;
+  template <typename T>
+  void build(const Csr<T>& A, bool lower) {
+    const int64_t n = A.n;
+    std::vector<int32_t> lev(n, 0);
+    int32_t maxl = -1;
+    auto visit = [&](int64_t i) {
+      int32_t l = 0;
+      for (int64_t k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+        const int64_t j = A.idx[k];
+        if (lower ? (j < i) : (j > i)) l = std::max(l, lev[j] + 1);
+      }
+      lev[i] = l;
+      maxl = std::max(maxl, l);
+    };
+    if (lower)
+      for (int64_t i = 0; i < n; ++i) visit(i);
+    else
+      for (int64_t i = n - 1; i >= 0; --i) visit(i);
+    ptr.assign(maxl + 2, 0);
+    rows.resize(n);
+    for (int64_t i = 0; i < n; ++i) ptr[lev[i] + 1]++;
+    for (int32_t l = 0; l <= maxl; ++l) ptr[l + 1] += ptr[l];
+    std::vector<int64_t> cur(ptr.begin(), ptr.end() - 1);
+    for (int64_t i = 0; i < n; ++i) rows[cur[lev[i]]++] = (int32_t)i;
+  }
+};
+
+// gauss_seidel.rs:111-125 row body with the operands of the two triangles taken from different
+// vectors: columns < row from `lo`, columns > row from `hi` (null: the entries multiply the zeros
+// of a sweep that starts from x = 0 and are skipped).  Same fold order as gs_row.
+template <typename T>
+inline T gs_row_split(const Csr<T>& A, int64_t row, T rhs_v, T diag, const T* lo, const T* hi) {
+  T sigma = zero_of(T());
+  for (int64_t k = A.indptr[row]; k < A.indptr[row + 1]; ++k) {
+    const int64_t col = A.idx[k];
+    if (col < row) {
+      if (lo) sigma = add(sigma, mul(A.a[k], lo[col]));
+    } else if (col > row) {
+      if (hi) sigma = add(sigma, mul(A.a[k], hi[col]));
+    }
+  }
+  return divi(sub(rhs_v, sigma), diag);
+}
+
 template <typename T>
 struct Precond {
   int kind;
@@ -306,6 +529,19 @@ struct Precond {
   real_t<T>* dinv_r;   // ORC_PC_DIAG_REAL: reciprocal (real)
   T* gs_diag;          // GS kinds: cached diagonal
   T* gs_tmp;           // GS_SYM: forward result
+  const Levels* lev_f; // modes >= 1: level schedules of the lower / upper pattern
+  const Levels* lev_b;
+  void level_sweep(const Levels& L, const T* rhs, const T* lo, const T* hi, T* out) const {
+    const int64_t nl = (int64_t)L.ptr.size() - 1;
+    for (int64_t l = 0; l < nl; ++l) {
+      const int64_t b = L.ptr[l], e = L.ptr[l + 1];
+#pragma omp parallel for schedule(static) if (e - b > 2048)
+      for (int64_t i = b; i < e; ++i) {
+        const int64_t r = L.rows[i];
+        out[r] = gs_row_split(*A, r, rhs[r], gs_diag[r], lo, hi);
+      }
+    }
+  }
   // precond.rs:48-52: *r = (*v) * (*s)
   void apply(const T* in, T* out) const {
     switch (kind) {
@@ -316,10 +552,19 @@ struct Precond {
         for (int64_t i = 0; i < n; ++i) out[i] = mul_real(in[i], dinv_r[i]);
         break;
       case ORC_PC_GS_FWD:
+        if (lev_f) {
+          level_sweep(*lev_f, in, out, nullptr, out);
+          break;
+        }
         zero_vec(n, out);
         for (int64_t r = 0; r < n; ++r) out[r] = gs_row(*A, r, in[r], gs_diag[r], out);
         break;
       case ORC_PC_GS_SYM:
+        if (lev_f && lev_b) {
+          level_sweep(*lev_f, in, gs_tmp, nullptr, gs_tmp);
+          level_sweep(*lev_b, in, gs_tmp, out, out);
+          break;
+        }
         // forward sweep from zero, then the same row body over rows n-1..0, in place.
         zero_vec(n, out);
         for (int64_t r = 0; r < n; ++r) out[r] = gs_row(*A, r, in[r], gs_diag[r], out);
@@ -342,6 +587,8 @@ struct PrecondOwner {
     p.dinv_r = nullptr;
     p.gs_diag = nullptr;
     p.gs_tmp = nullptr;
+    p.lev_f = nullptr;
+    p.lev_b = nullptr;
     ok = true;
     bad_row = -1;
     if (kind == ORC_PC_DIAG) {
@@ -357,8 +604,18 @@ struct PrecondOwner {
       p.gs_diag = new T[n];
       bad_row = gs_diagonals(*A, p.gs_diag);
       ok = bad_row < 0;
+      if (ok && g_mode >= 1) {
+        lev_f.build(*A, true);
+        p.lev_f = &lev_f;
+        if (kind == ORC_PC_GS_SYM) {
+          lev_b.build(*A, false);
+          p.lev_b = &lev_b;
+          p.gs_tmp = new T[n];
+        }
+      }
     }
   }
+  Levels lev_f, lev_b;
   ~PrecondOwner() {
     delete[] p.dinv_t;
     delete[] p.dinv_r;
@@ -654,6 +911,7 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
     b_norm += square(rhs[row]);                 // :83
     x[row] = divi(sub(rhs[row], sigma), d);     // :84
   }
+  if (g_mode == 3) b_norm = exact_sumsq(n, rhs);  // exact-dot flavour: the same sum, rounded once
   const R tol2 = (R)eps * std::sqrt(b_norm);  // :87
   A.mul_vec(x, res);                            // :90
   axpy(n, neg(one_of(T())), rhs, res);          // :97
@@ -902,30 +1160,16 @@ void orc_axpy_s(int64_t n, float a, const float* x, float* y) {
 void orc_axpby_s(int64_t n, float a, const float* x, float b, float* y) {
   for (int64_t i = 0; i < n; ++i) y[i] = x[i] * a + y[i] * b;
 }
-float orc_conj_dot_s(int64_t n, const float* x, const float* y) {
-  float acc = 0.f;
-  for (int64_t i = 0; i < n; ++i) acc = acc + x[i] * y[i];
-  return acc;
-}
+float orc_conj_dot_s(int64_t n, const float* x, const float* y) { return conj_dot<float>(n, x, y); }
 void orc_dot_c(int64_t n, const float* x, const float* y, float* out) {
-  float re = 0.f, im = 0.f;
-  for (int64_t i = 0; i < n; ++i) {
-    float ar = x[2 * i], ai = x[2 * i + 1], br = y[2 * i], bi = y[2 * i + 1];
-    re = re + (ar * br - ai * bi);
-    im = im + (ar * bi + ai * br);
-  }
-  out[0] = re;
-  out[1] = im;
+  const cplxf r = dot_fb<cplxf>(n, (const cplxf*)x, (const cplxf*)y);
+  out[0] = r.re;
+  out[1] = r.im;
 }
 void orc_conj_dot_c(int64_t n, const float* x, const float* y, float* out) {
-  float re = 0.f, im = 0.f;
-  for (int64_t i = 0; i < n; ++i) {
-    float ar = x[2 * i], ai = -x[2 * i + 1], br = y[2 * i], bi = y[2 * i + 1];
-    re = re + (ar * br - ai * bi);
-    im = im + (ar * bi + ai * br);
-  }
-  out[0] = re;
-  out[1] = im;
+  const cplxf r = conj_dot<cplxf>(n, (const cplxf*)x, (const cplxf*)y);
+  out[0] = r.re;
+  out[1] = r.im;
 }
 
 void orc_diag_apply_d(int64_t n, const double* diag, const double* in, double* out) {

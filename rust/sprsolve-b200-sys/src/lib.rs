@@ -8,7 +8,8 @@
 use cauchy::Scalar;
 use num_complex::Complex64;
 use sprs::CsMatI;
-use sprsolve::{MatVecMul, SolveResult, SolverError};
+use sprsolve::error::{SolveResult, SolverError};
+use sprsolve::MatVecMul;
 use std::ffi::CStr;
 use std::marker::PhantomData;
 use std::os::raw::{c_char, c_double, c_int, c_void};

@@ -35,7 +35,7 @@ __device__ __forceinline__ void hist_put(StateHead& h, double* hist, long long c
 
 // ---------------------------------------------------------------- scalar kernels (1 thread)
 template <typename T>
-__global__ void bicg_s_rhs(BicgState<T>* st, const scal2* red) {
+__device__ __forceinline__ void bicg_s_rhs_body(BicgState<T>* st, const scal2* red) {
   const double rhs_norm = sqrt(red[0].re);  // norm2(rhs), :225
   st->rhs_norm = rhs_norm;
   st->tol2 = st->tol * rhs_norm;            // :231
@@ -46,9 +46,14 @@ __global__ void bicg_s_rhs(BicgState<T>* st, const scal2* red) {
   }
 }
 
+template <typename T>
+__global__ void bicg_s_rhs(BicgState<T>* st, const scal2* red) {
+  bicg_s_rhs_body(st, red);
+}
+
 // after r = A x - rhs, r0 = r: used for the start (:251-259) and for the restart (:315-317)
 template <typename T>
-__global__ void bicg_s_init(BicgState<T>* st, const scal2* red, double* hist, long long cap, int restart) {
+__device__ __forceinline__ void bicg_s_init_body(BicgState<T>* st, const scal2* red, double* hist, long long cap, int restart) {
   if (restart ? st->h.status != DS_NEED_RESTART : st->h.status != DS_RUNNING) return;
   const double rn = sqrt(red[0].re);
   if (!restart) {
@@ -73,7 +78,12 @@ __global__ void bicg_s_init(BicgState<T>* st, const scal2* red, double* hist, lo
 }
 
 template <typename T>
-__global__ void bicg_s1(BicgState<T>* st, const scal2* red, double* hist, long long cap) {
+__global__ void bicg_s_init(BicgState<T>* st, const scal2* red, double* hist, long long cap, int restart) {
+  bicg_s_init_body(st, red, hist, cap, restart);
+}
+
+template <typename T>
+__device__ __forceinline__ void bicg_s1_body(BicgState<T>* st, const scal2* red, double* hist, long long cap) {
   if (st->h.status != DS_RUNNING) return;
   const long long its = ++st->h.its;
   const double r_norm = sqrt(red[0].re);  // :296
@@ -94,6 +104,11 @@ __global__ void bicg_s1(BicgState<T>* st, const scal2* red, double* hist, long l
   const T beta = mul(divi(st->rho, st->rho_old), divi(st->alpha, st->w));  // :319
   st->beta = beta;
   st->c_pv = mul(neg(beta), st->w);  // -beta * w, :324
+}
+
+template <typename T>
+__global__ void bicg_s1(BicgState<T>* st, const scal2* red, double* hist, long long cap) {
+  bicg_s1_body(st, red, hist, cap);
 }
 
 template <typename T>
@@ -200,6 +215,242 @@ bicg_k3(const BicgState<T>* st, int64_t n, T* x, const T* y, const T* z, T* r, c
   write_partials(e0, e1, partials);
 }
 
+// ---------------------------------------------------------------- single-kernel solve (L2-resident systems)
+// On a system whose matrix and vectors fit in L2 one iteration is a few microseconds of work and the
+// multi-kernel loop above is bound by per-kernel latency (~5-12 us x 9.5 launches: 63 us on the 512^2
+// reference matrix, independent of n).  Here the WHOLE solve -- ||b||, r = A x - b, the unrolled first
+// iteration, the loop with its convergence / restart / breakdown tests, the residual history -- is ONE
+// cooperative kernel: one CTA per SM, a thread owns the same rows in every phase, phases are separated
+// by a grid barrier (one atomic + one spin per CTA) only where a vector written by other CTAs is
+// gathered (before each SpMV) or a reduction completes.  Every CTA sums the per-CTA double-double
+// partials of a reduction point itself (same fixed order, one rounding), so the Krylov scalars are
+// replicated in shared memory and no second barrier or broadcast is needed.
+// Same element-wise operations and exactly rounded sums as the multi-kernel path => the same bits.
+template <typename T>
+struct FusedArgs {
+  const int* indptr;
+  const int* cols;
+  const T* vals;
+  int n;
+  const T* rhs;
+  T *x, *r, *r0, *p, *y, *v, *t, *z;
+  const void* dinv;
+  BicgState<T>* st;         // final state (written by CTA 0)
+  Acc<T>* parts;            // [3][2 * gridDim.x]
+  unsigned long long* bar;  // grid barrier counter, zeroed before the launch
+  double* hist;
+  long long cap, max_iter;
+  double tol;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// vectors other CTAs write during the kernel are read at L2 (the L1 of an SM is not coherent)
+__device__ __forceinline__ double ld_l2(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ cplx ld_l2(const cplx* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return cplx{v.x, v.y};
+}
+__device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }
+__device__ __forceinline__ cplx ld_ro(const cplx* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return cplx{v.x, v.y};
+}
+__device__ __forceinline__ Acc<double> ld_l2(const Acc<double>* p) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return Acc<double>{v.x, v.y};
+}
+__device__ __forceinline__ Acc<cplx> ld_l2(const Acc<cplx>* p) {
+  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  return Acc<cplx>{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ scal2 acc_round(const Acc<double>& a) { return scal2{a.hi + a.lo, 0.0}; }
+__device__ __forceinline__ scal2 acc_round(const Acc<cplx>& a) { return scal2{a.rh + a.rl, a.ih + a.il}; }
+
+// One CSR row folded sequentially in CSR order (src/mat.rs:100-105); matrix through the read-only path
+// (constant for the whole kernel, L1-resident after the first iteration), x at L2.
+template <typename T>
+__device__ __forceinline__ T fused_row(const FusedArgs<T>& a, int i, const T* src) {
+  const int p0 = __ldg(a.indptr + i), p1 = __ldg(a.indptr + i + 1);
+  T acc = zero_of<T>();
+  for (int k = p0; k < p1; k += 4) {
+    int c[4];
+    T m[4], xv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kk = min(k + j, p1 - 1);
+      c[j] = __ldg(a.cols + kk);
+      m[j] = ld_ro(a.vals + kk);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xv[j] = ld_l2(src + c[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (k + j < p1) acc = add(acc, mul(xv[j], m[j]));
+  }
+  return acc;
+}
+
+template <typename T, typename V, bool PC, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T> a) {
+  __shared__ BicgState<T> S;
+  __shared__ scal2 red[2];
+  __shared__ Acc<T> scratch[32];
+  const int tid = threadIdx.x;
+  const int gtid = blockIdx.x * BLOCK + tid, nth = gridDim.x * BLOCK, n = a.n;
+  const V* dinv = static_cast<const V*>(a.dinv);
+  double* hist = blockIdx.x == 0 ? a.hist : nullptr;  // one writer
+  unsigned long long target = 0;
+  int rp = 0;  // reduction points cycle through three partial buffers (a buffer is re-written two barriers later)
+
+  auto grid_sync = [&]() {
+    __syncthreads();
+    if (tid == 0) {
+      target += gridDim.x;
+      __threadfence();
+      atomicAdd(a.bar, 1ULL);
+      while (ld_acquire_gpu_u64(a.bar) < target) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+  };
+  // this CTA's partials of a reduction point; after the barrier every CTA sums all of them in the same
+  // fixed order and rounds once -> red[0], red[1] (identical in every CTA)
+  auto reduce = [&](Acc<T> e0, Acc<T> e1) {
+    e0 = block_sum(e0, scratch);
+    e1 = block_sum(e1, scratch);
+    Acc<T>* pb = a.parts + (size_t)rp * 2 * gridDim.x;
+    if (tid == 0) {
+      pb[2 * blockIdx.x] = e0;
+      pb[2 * blockIdx.x + 1] = e1;
+    }
+    grid_sync();
+    for (int slot = 0; slot < 2; ++slot) {
+      Acc<T> acc = zero_of<Acc<T>>();
+      for (int i = tid; i < (int)gridDim.x; i += BLOCK) acc = add(acc, ld_l2(pb + 2 * i + slot));
+      acc = block_sum(acc, scratch);
+      if (tid == 0) red[slot] = acc_round(acc);
+    }
+    rp = rp == 2 ? 0 : rp + 1;
+    __syncthreads();
+  };
+  // r = A x - rhs ; r0 = r ; ||r||^2   (:243-251, and the restart :305-316)
+  auto residual = [&](int restart) {
+    Acc<T> e0 = zero_of<Acc<T>>();
+    const T m1 = neg(one_of<T>());
+    for (int i = gtid; i < n; i += nth) {
+      const T ri = add(fused_row(a, i, a.x), mul(a.rhs[i], m1));
+      a.r[i] = ri;
+      a.r0[i] = ri;
+      acc_sq(e0, ri);
+    }
+    reduce(e0, zero_of<Acc<T>>());
+    if (tid == 0) bicg_s_init_body(&S, red, hist, a.cap, restart);
+    __syncthreads();
+  };
+  // everything of an iteration after the S1 test; returns false when the solve ended (breakdown)
+  auto iteration = [&](bool first) -> bool {
+    {  // K1
+      const T c_pv = S.c_pv, beta = S.beta, one = one_of<T>();
+      for (int i = gtid; i < n; i += nth) {
+        T pi;
+        if (first) {
+          pi = a.r[i];
+        } else {
+          pi = add(mul(a.v[i], c_pv), mul(a.p[i], beta));
+          pi = add(pi, mul(a.r[i], one));
+        }
+        a.p[i] = pi;
+        if (PC) a.y[i] = mul_diag(pi, dinv[i]);
+      }
+    }
+    grid_sync();  // y complete
+    {  // v = A y, <r0, v>
+      Acc<T> e0 = zero_of<Acc<T>>();
+      for (int i = gtid; i < n; i += nth) {
+        const T vi = fused_row(a, i, a.y);
+        a.v[i] = vi;
+        acc_prod(e0, conj_of(a.r0[i]), vi);
+      }
+      reduce(e0, zero_of<Acc<T>>());
+    }
+    if (tid == 0) bicg_s2_body(&S, red, first ? 1 : 0);
+    __syncthreads();
+    if (S.h.status != DS_RUNNING) return false;
+    {  // K2
+      const T nalpha = S.nalpha;
+      for (int i = gtid; i < n; i += nth) {
+        const T ri = add(a.r[i], mul(a.v[i], nalpha));
+        a.r[i] = ri;
+        if (PC) a.z[i] = mul_diag(ri, dinv[i]);
+      }
+    }
+    grid_sync();  // z complete
+    {  // t = A z, <t,t>, <t,r>
+      Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
+      for (int i = gtid; i < n; i += nth) {
+        const T ti = fused_row(a, i, a.z);
+        a.t[i] = ti;
+        const T cy = conj_of(ti);
+        acc_prod(e0, cy, ti);
+        acc_prod(e1, cy, a.r[i]);
+      }
+      reduce(e0, e1);
+    }
+    if (tid == 0) bicg_s3_body(&S, red);
+    __syncthreads();
+    {  // K3 + the partials of the next iteration's test
+      Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
+      const T nalpha = S.nalpha, nw = S.nw;
+      for (int i = gtid; i < n; i += nth) {
+        const T zi = a.z[i];
+        T xi = add(a.x[i], mul(a.y[i], nalpha));
+        xi = add(xi, mul(zi, nw));
+        a.x[i] = xi;
+        const T ri = add(a.r[i], mul(a.t[i], nw));
+        a.r[i] = ri;
+        acc_sq(e0, ri);
+        acc_prod(e1, conj_of(a.r0[i]), ri);
+      }
+      reduce(e0, e1);
+    }
+    return true;
+  };
+
+  if (tid == 0) {
+    memset(&S, 0, sizeof(S));
+    S.h.status = DS_RUNNING;
+    S.tol = a.tol;
+  }
+  __syncthreads();
+  {  // ||b||  (:225-231)
+    Acc<T> e0 = zero_of<Acc<T>>();
+    for (int i = gtid; i < n; i += nth) acc_sq(e0, a.rhs[i]);
+    reduce(e0, zero_of<Acc<T>>());
+    if (tid == 0) bicg_s_rhs_body(&S, red);
+    __syncthreads();
+  }
+  if (S.h.status == DS_ZERO_RHS) {
+    for (int i = gtid; i < n; i += nth) a.x[i] = zero_of<T>();
+  } else {
+    residual(0);
+    if (S.h.status == DS_RUNNING && iteration(true)) {
+      for (long long k = 1; k < a.max_iter; ++k) {  // :295
+        if (tid == 0) bicg_s1_body(&S, red, hist, a.cap);
+        __syncthreads();
+        if (S.h.status == DS_NEED_RESTART) residual(1);  // sets the status back to running
+        if (S.h.status != DS_RUNNING) break;
+        if (!iteration(false)) break;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) *a.st = S;
+}
+
 // ---------------------------------------------------------------- host driver
 template <typename T>
 struct BicgStab : spb_solver {
@@ -208,6 +459,21 @@ struct BicgStab : spb_solver {
   DevBuf red;       // scal2 [2]
   DevBuf state;     // BicgState<T>
   DevBuf hist_d;
+  DevBuf fused_parts, fused_bar;  // single-kernel path
+
+  // Single-kernel solve: one GPU, Jacobi or no preconditioner, matrix + vectors resident in L2.
+  bool fused_eligible(const CsrMat<T>* Am, PcMode pcm) const {
+    const char* e = getenv("SPB_FUSED");
+    if (e && *e == '0') return false;
+    if (ctx->dist || Am->ip64 || Am->n_halo > 0 || pcm == PCM_GENERIC || size <= 0) return false;
+    if (e && *e == '1') return true;
+    const char* mb = getenv("SPB_FUSED_MAX_MB");
+    const double limit = (mb && *mb ? atof(mb) : 48.0) * 1048576.0;
+    const double bytes = (double)Am->nnz * (sizeof(T) + 4) + 10.0 * (double)size * sizeof(T);
+    return bytes <= limit;
+  }
+  template <typename V, bool PC>
+  void launch_fused(const FusedArgs<T>& fa0, int64_t n);
 
   BicgStab(spb_op* A_, int64_t size_) {
     A = A_;
@@ -265,6 +531,39 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   init.h.status = DS_RUNNING;
   init.tol = tol;
   SPB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+
+  if (fused_eligible(Am, pcm)) {
+    // the whole solve in one cooperative kernel (see bicg_fused_kernel)
+    FusedArgs<T> fa{bufptr<int>(Am->indptr), bufptr<int>(Am->cols), bufptr<T>(Am->vals), (int)n, rhs, x, r, r0, p, y, v, t, z,
+                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol};
+    c->gate = nullptr;
+    if (pcm == PCM_JACOBI)
+      launch_fused<T, true>(fa, n);
+    else if (pcm == PCM_JACOBI_REAL)
+      launch_fused<double, true>(fa, n);
+    else
+      launch_fused<T, false>(fa, n);
+    BicgState<T> fin;
+    SPB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    int rcf;
+    if (fin.h.status == DS_OK || fin.h.status == DS_ZERO_RHS) {
+      *iters = fin.h.res_iters;
+      *resid = fin.h.res_resid;
+      rcf = SPB_OK;
+    } else if (fin.h.status == DS_BREAKDOWN) {
+      *iters = fin.h.res_iters;
+      rcf = SPB_BREAKDOWN;
+    } else {
+      *iters = max_iter;
+      rcf = SPB_INSUFFICIENT_ITER;
+    }
+    const int64_t hl = fin.h.status == DS_ZERO_RHS ? 0 : fin.h.hist_len;
+    if (hist_len) *hist_len = hl;
+    if (hd && hl > 0)
+      SPB_CUDA(cudaMemcpy(hist, hd, sizeof(double) * std::min<int64_t>(hl, cap), cudaMemcpyDeviceToHost));
+    return rcf;
+  }
 
   auto scalar = [&](auto kernel, auto... args) {
     LaunchScope ls(c, FAM_SCALAR);
@@ -417,6 +716,37 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     throw;
   }
   return rc;
+}
+
+template <typename T>
+template <typename V, bool PC>
+void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
+  Ctx* c = ctx;
+  FusedArgs<T> fa = fa0;
+  const char* be = getenv("SPB_FUSED_BLOCK");
+  const int block = be && *be ? atoi(be) : 512;
+  auto run = [&](auto kern, int BLOCK) {
+    int bps = 0;
+    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BLOCK, 0));
+    if (bps < 1) SPB_FAIL(SPB_CUDA_ERROR, "single-kernel BiCGStab does not fit on an SM");
+    const char* ge = getenv("SPB_FUSED_CTAS_PER_SM");
+    const int per_sm = std::max(1, std::min(bps, ge && *ge ? atoi(ge) : 1));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count * per_sm, ceil_div(n, BLOCK)));
+    fused_parts.ensure(sizeof(Acc<T>) * 6 * (size_t)grid);
+    fused_bar.ensure(sizeof(unsigned long long) * 2);
+    fa.parts = bufptr<Acc<T>>(fused_parts);
+    fa.bar = bufptr<unsigned long long>(fused_bar);
+    SPB_CUDA(cudaMemsetAsync(fused_bar.p, 0, sizeof(unsigned long long) * 2, c->stream));
+    LaunchScope ls(c, FAM_VEC);
+    void* args[] = {(void*)&fa};
+    SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(BLOCK), args, 0, c->stream));
+  };
+  if (block >= 1024)
+    run(bicg_fused_kernel<T, V, PC, 1024>, 1024);
+  else if (block >= 512)
+    run(bicg_fused_kernel<T, V, PC, 512>, 512);
+  else
+    run(bicg_fused_kernel<T, V, PC, 256>, 256);
 }
 
 spb_solver* make_bicgstab(spb_op* A, int64_t size) {

@@ -65,6 +65,8 @@ int spb_init(int device, spb_ctx** out) {
   SPB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
   SPB_CUDA(cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming));
   SPB_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+  SPB_CUDA(cudaMalloc(&c->dev_err, 4 * sizeof(int)));
+  SPB_CUDA(cudaMemset(c->dev_err, 0, 4 * sizeof(int)));
   *out = c;
   return SPB_OK;
   SPB_CATCH
@@ -91,6 +93,7 @@ int spb_finalize(spb_ctx* c) {
   cudaStreamDestroy(c->comm_stream);
   cudaEventDestroy(c->ev_pack);
   cudaEventDestroy(c->ev_halo);
+  if (c->dev_err) cudaFree(c->dev_err);
   delete c;
   return SPB_OK;
   SPB_CATCH
@@ -114,6 +117,7 @@ int spb_synchronize(spb_ctx* c) {
   use_device(c);
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->comm_stream));
+  device_check(c);  // a bounded device-side spin that timed out (dead peer, stalled sweep) surfaces here
   return SPB_OK;
   SPB_CATCH
 }
@@ -482,7 +486,7 @@ static void op_mul_host(spb_op* op, const void* v_in, void* v_out, bool with_dot
   if (n) SPB_CUDA(cudaMemcpyAsync(din.p, v_in, sizeof(T) * n, cudaMemcpyHostToDevice, c->stream));
   op_mul_dev<T>(op, bufptr<T>(din), bufptr<T>(dout), with_dot, dot_out);
   if (n) SPB_CUDA(cudaMemcpyAsync(v_out, dout.p, sizeof(T) * n, cudaMemcpyDeviceToHost, c->stream));
-  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  device_check(c);  // synchronises; a timed-out halo / sweep spin must not hand back stale data as SPB_OK
 }
 
 static int op_mul_checked(spb_op* op, const void* v_in, int64_t n_in, void* v_out, int64_t n_out,
@@ -827,7 +831,7 @@ int spb_solver_solve_dev(spb_solver* s, spb_op* precond, const void* d_rhs, void
   if (hist_len) *hist_len = 0;
   if (precond && precond->dtype != s->dtype) SPB_FAIL(SPB_INVALID_ARG, "preconditioner dtype mismatch");
   const int rc = s->solve_dev(precond, d_rhs, d_x, max_iter, tol, iters, resid, hist, hist_cap, hist_len);
-  peer_check(s->ctx);
+  device_check(s->ctx);
   return rc;
   SPB_CATCH
 }
@@ -862,7 +866,7 @@ int spb_solver_solve(spb_solver* s, spb_op* precond, const void* rhs, int64_t n_
     SPB_CUDA(cudaMemcpyAsync(s->stage_x.p, x, esz * n_rhs, cudaMemcpyHostToDevice, c->stream));
   }
   const int rc = s->solve_dev(precond, s->stage_rhs.p, s->stage_x.p, max_iter, tol, iters, resid, hist, hist_cap, hist_len);
-  peer_check(c);
+  device_check(c);
   if (n_rhs) SPB_CUDA(cudaMemcpyAsync(x, s->stage_x.p, esz * n_rhs, cudaMemcpyDeviceToHost, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   return rc;

@@ -57,6 +57,7 @@ struct Ctx {
   // *gate == gate_value (iterations queued past convergence become no-ops).
   const int* gate = nullptr;
   int gate_value = -1;
+  int* dev_err = nullptr;  // device word set by kernels whose bounded spins timed out (1 halo, 2 Gauss-Seidel)
   void* pinned = nullptr;  // small pinned scratch for status / scalar read-backs
   size_t pinned_bytes = 0;
 

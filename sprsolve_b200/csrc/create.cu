@@ -116,6 +116,38 @@ __global__ void narrow_indptr_kernel(const int64_t* in, int64_t n1, int* out) {
   if (i < n1) out[i] = (int)in[i];
 }
 
+// Structural validation of caller-supplied index arrays (sprs::CsMat::new rejects such input before
+// any solver of the reference sees it): every column id must lie in [0, ncols).
+__global__ void validate_cols_kernel(const int* cols, int64_t nnz, int ncols, int* bad) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < nnz; k += (int64_t)gridDim.x * blockDim.x)
+    if ((unsigned)cols[k] >= (unsigned)ncols) atomicExch(bad, 1);  // integer flag: order-independent
+}
+
+void validate_device_cols(Ctx* ctx, const int* cols, int64_t nnz, int64_t ncols) {
+  if (nnz <= 0) return;
+  DevBuf bad;
+  bad.alloc(sizeof(int));
+  SPB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+  {
+    LaunchScope ls(ctx, FAM_SCALAR);
+    const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)ctx->sm_count * 16);
+    validate_cols_kernel<<<grid, 256, 0, ctx->stream>>>(cols, nnz, (int)ncols, bufptr<int>(bad));
+    check_launch("validate_cols_kernel");
+  }
+  int h = 0;
+  SPB_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SPB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h) SPB_FAIL(SPB_INCOMPATIBLE_FORMAT, "column index out of range");
+}
+
+// indptr[0] == 0, non-decreasing (host array of n1 entries)
+template <typename IP>
+static void validate_host_indptr(const IP* ip, int64_t n1) {
+  if (n1 < 1 || ip[0] != 0) SPB_FAIL(SPB_INCOMPATIBLE_FORMAT, "indptr must start at 0");
+  for (int64_t i = 1; i < n1; ++i)
+    if (ip[i] < ip[i - 1]) SPB_FAIL(SPB_INCOMPATIBLE_FORMAT, "indptr must be non-decreasing");
+}
+
 template <typename T>
 static void finish_create(CsrMat<T>* m) {
   if (m->ctx->dist)
@@ -133,7 +165,12 @@ CsrMat<T>* csr_from_host(Ctx* ctx, int64_t n_global, int64_t row_begin, int64_t 
     SPB_FAIL(SPB_INVALID_ARG, "bad row range");
   if (n_global >= (int64_t)1 << 31) SPB_FAIL(SPB_INVALID_ARG, "matrix dimension exceeds int32 columns");
   const int64_t nl = row_end - row_begin;
+  if (indptr_bits == 64)
+    validate_host_indptr((const int64_t*)indptr, nl + 1);
+  else
+    validate_host_indptr((const int32_t*)indptr, nl + 1);
   const int64_t nnz = indptr_bits == 64 ? ((const int64_t*)indptr)[nl] : (int64_t)((const int32_t*)indptr)[nl];
+  if (nnz > 0 && (!indices || !values)) SPB_FAIL(SPB_INVALID_ARG, "null index / value array");
   auto* m = new CsrMat<T>();
   try {
     m->ctx = ctx;
@@ -168,6 +205,7 @@ CsrMat<T>* csr_from_host(Ctx* ctx, int64_t n_global, int64_t row_begin, int64_t 
       SPB_CUDA(cudaMemcpyAsync(m->vals.p, values, sizeof(T) * nnz, cudaMemcpyHostToDevice, ctx->stream));
     }
     SPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    validate_device_cols(ctx, bufptr<int>(m->cols), nnz, n_global);  // before localisation / analysis index with them
     finish_create(m);
   } catch (...) {
     delete m;

@@ -29,6 +29,7 @@ struct PutArgs {
   void* dst0[kMaxPeers];                 // peer's halo payload + my offset in it (parity 0), T*
   long long dst_stride[kMaxPeers];       // peer's n_halo: parity 1 lives dst_stride elements further
   unsigned long long* rflag[kMaxPeers];  // &peer_head->flags[my rank]
+  unsigned long long* rack[kMaxPeers];   // &peer_head->acks[my rank]
   long long send_off[kMaxPeers + 1];     // into send_idx
 };
 

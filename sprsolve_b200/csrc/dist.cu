@@ -146,13 +146,22 @@ void window_destroy(PeerWindow* w) {
   delete w;
 }
 
-void peer_check(Ctx* ctx) {
-  if (!peer_mode(ctx)) return;
-  ScalWin* me = static_cast<ScalWin*>(ctx->dist->scal->local);
-  int err = 0;
-  SPB_CUDA(cudaMemcpyAsync(&err, &me->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+void device_check(Ctx* ctx) {
+  int err = 0, dev = 0;
+  if (peer_mode(ctx)) {
+    ScalWin* me = static_cast<ScalWin*>(ctx->dist->scal->local);
+    SPB_CUDA(cudaMemcpyAsync(&err, &me->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (ctx->dev_err) SPB_CUDA(cudaMemcpyAsync(&dev, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   SPB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (err || dev) {  // report once: clear the words so that the context stays usable for diagnostics
+    if (err) cudaMemsetAsync(&static_cast<ScalWin*>(ctx->dist->scal->local)->error, 0, sizeof(int), ctx->stream);
+    if (dev) cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
   if (err) SPB_FAIL(SPB_NCCL_ERROR, "timed out waiting for a peer rank (scalar all-reduce over peer memory)");
+  if (dev == 1) SPB_FAIL(SPB_NCCL_ERROR, "timed out waiting for a neighbour's halo put (peer memory)");
+  if (dev) SPB_FAIL(SPB_CUDA_ERROR, "Gauss-Seidel wavefront sweep: timed out waiting for a value of another block");
 }
 
 void allgather_i64(Ctx* ctx, const int64_t* host_in, size_t count, std::vector<int64_t>& out) {
@@ -239,9 +248,23 @@ __global__ void pack_kernel(const T* x, const int* idx, int64_t n, T* out) {
 // neighbours' halo windows over NVLink; the CTA that finishes last publishes the sequence number
 // to every neighbour (release, system scope).
 template <typename T>
-__global__ void halo_put_kernel(const T* x, const int* idx, long long total, HaloHead* head, PutArgs pa) {
+__global__ void halo_put_kernel(const T* x, const int* idx, long long total, HaloHead* head, PutArgs pa, int* err) {
   const unsigned long long seq = *((volatile unsigned long long*)&head->seq) + 1;
   const long long par = (long long)(seq & 1);
+  if (threadIdx.x == 0) {
+    // this rank's SpMV seq-1 is complete (stream order): acknowledge it to every peer, THEN wait until
+    // every peer has consumed exchange seq-2, the previous user of the parity buffer written below
+    // (publish before waiting: no cycle).  Every CTA waits; block 0 publishes.
+    if (blockIdx.x == 0)
+      for (int j = 0; j < pa.npeers; ++j) st_release_sys(pa.rack[j], seq - 1);
+    if (seq >= 3)
+      for (int j = 0; j < pa.npeers; ++j)
+        if (!spin_until_ge(&head->acks[head->peer_rank[j]], seq - 2)) {
+          head->error = 1;
+          if (err) *err = 1;
+        }
+  }
+  __syncthreads();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     int j = 0;
@@ -269,7 +292,7 @@ void halo_put(CsrMat<T>* m, const T* x) {
   LaunchScope ls(c, FAM_PACK);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), 148 * 4));
   halo_put_kernel<T><<<grid, 256, 0, c->stream>>>(x, bufptr<int>(m->send_idx), total,
-                                                   static_cast<HaloHead*>(m->halo_win->local), m->put);
+                                                   static_cast<HaloHead*>(m->halo_win->local), m->put, c->dev_err);
   check_launch("halo_put_kernel");
 }
 
@@ -372,6 +395,7 @@ void csr_localize(CsrMat<T>* m) {
       pa.dst0[j] = qbase + kHaloHeadBytes + sizeof(T) * (size_t)roff;
       pa.dst_stride[j] = std::max<int64_t>(nh_all[q], 1);
       pa.rflag[j] = &reinterpret_cast<HaloHead*>(qbase)->flags[me];
+      pa.rack[j] = &reinterpret_cast<HaloHead*>(qbase)->acks[me];
       pa.send_off[j] = hp.send_off;
     }
     pa.send_off[pa.npeers] = total_send;

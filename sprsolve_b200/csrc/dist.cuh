@@ -70,8 +70,10 @@ struct Dist {
 };
 
 inline bool peer_mode(const Ctx* ctx) { return ctx->dist && ctx->dist->peer; }
-// Raises SPB_NCCL_ERROR if a device-side spin on a peer flag timed out since the last check.
-void peer_check(Ctx* ctx);
+// Raises SPB_NCCL_ERROR / SPB_CUDA_ERROR if a device-side spin timed out since the last check (scalar
+// all-reduce window, halo put / halo flags, Gauss-Seidel cross-block hand-off) and clears the flag.
+// Synchronises the stream.
+void device_check(Ctx* ctx);
 
 // In-place sum of `count` (<= 4) doubles across ranks on the compute stream (no-op when single
 // GPU).  Peer transport: one 32-thread kernel; NCCL transport: ncclAllReduce.

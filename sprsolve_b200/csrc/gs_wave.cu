@@ -132,14 +132,17 @@ __device__ __forceinline__ cplx wv_lds<cplx>(uint32_t addr) {
 // x value at a resolved shared-memory address; spins while the slot still holds the sentinel
 // (a cross-block value the helper warps have not delivered yet).
 template <typename T>
-__device__ __forceinline__ T wv_x(uint32_t addr, int* flag, long long& spins) {
+__device__ __forceinline__ T wv_x(uint32_t addr, int* flag, int* err, long long& spins) {
   T x = wv_lds<T>(addr);
   if (wv_is_sentinel(x)) {
     long long n = 0;
     do {
       x = wv_lds<T>(addr);
     } while (wv_is_sentinel(x) && ++n < (1LL << 26));
-    if (wv_is_sentinel(x)) *flag = 1;  // a legitimate value that equals the sentinel (a NaN): use it
+    if (wv_is_sentinel(x)) {  // a legitimate value that equals the sentinel (a NaN), or a stalled producer: use it, report it
+      flag[0] = 1;
+      if (err) *err = 2;
+    }
     spins += n;
   }
   return x;
@@ -160,6 +163,7 @@ struct WaveArgs {
   long long* stats;  // null, or [4 * nblocks]: clocks total / waiting for the ring / shared-memory spins / thread 0 in the level barrier
   const int* gate;
   int gate_value;
+  int* err;  // Ctx::dev_err
 };
 
 // Pre-pass (fully parallel): sentinel-fill the mailbox, permute rhs into sweep order, reduce the other
@@ -335,10 +339,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
           const T v2 = eval[(e + 2) * nrows + i], v3 = eval[(e + 3) * nrows + i];
           T x0 = wv_lds<T>(sbase + o0), x1 = wv_lds<T>(sbase + o1), x2 = wv_lds<T>(sbase + o2), x3 = wv_lds<T>(sbase + o3);
           if (wv_is_sentinel(x0) | wv_is_sentinel(x1) | wv_is_sentinel(x2) | wv_is_sentinel(x3)) {  // rare: wait for a neighbour block
-            x0 = wv_x<T>(sbase + o0, a.ticket + 1, spins);
-            x1 = wv_x<T>(sbase + o1, a.ticket + 1, spins);
-            x2 = wv_x<T>(sbase + o2, a.ticket + 1, spins);
-            x3 = wv_x<T>(sbase + o3, a.ticket + 1, spins);
+            x0 = wv_x<T>(sbase + o0, a.ticket + 1, a.err, spins);
+            x1 = wv_x<T>(sbase + o1, a.ticket + 1, a.err, spins);
+            x2 = wv_x<T>(sbase + o2, a.ticket + 1, a.err, spins);
+            x3 = wv_x<T>(sbase + o3, a.ticket + 1, a.err, spins);
           }
           sigma = add(sigma, mul(v0, x0));
           sigma = add(sigma, mul(v1, x1));
@@ -817,12 +821,10 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   a.stats = M->wave_stats.p ? bufptr<long long>(M->wave_stats) : nullptr;
   a.gate = c->gate;
   a.gate_value = c->gate_value;
+  a.err = c->dev_err;
   auto kern = ws.backward ? gs_wave_kernel<T, true> : gs_wave_kernel<T, false>;
-  static size_t attr_set[2] = {0, 0};
-  if (attr_set[ws.backward ? 1 : 0] < ws.smem_bytes) {
-    SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem_bytes));
-    attr_set[ws.backward ? 1 : 0] = ws.smem_bytes;
-  }
+  // per launch, not cached: the attribute is per device and a process may hold contexts on several
+  SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem_bytes));
   LaunchScope lsc(c, FAM_PRECOND);
   kern<<<ws.nblocks, WAVE_THREADS, ws.smem_bytes, c->stream>>>(a);
   check_launch("gs_wave_kernel");

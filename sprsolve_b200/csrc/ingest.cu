@@ -179,6 +179,13 @@ CsrMat<T>* csr_from_triplets(Ctx* c, int64_t n, int64_t nnz, const int32_t* rows
 template <typename T>
 CsrMat<T>* csr_from_csc(Ctx* c, int64_t n, const void* indptr, int indptr_bits, const int32_t* row_indices, const void* vals) {
   if (indptr_bits != 32 && indptr_bits != 64) SPB_FAIL(SPB_INVALID_ARG, "indptr_bits must be 32 or 64");
+  // the column pointers index the row-index / value arrays: indptr[0] == 0 and non-decreasing, else the
+  // expansion kernel writes out of bounds (the row indices themselves are range-checked by assemble())
+  for (int64_t i = 0; i <= n; ++i) {
+    const int64_t v = indptr_bits == 64 ? ((const int64_t*)indptr)[i] : (int64_t)((const int32_t*)indptr)[i];
+    const int64_t prev = i == 0 ? 0 : (indptr_bits == 64 ? ((const int64_t*)indptr)[i - 1] : (int64_t)((const int32_t*)indptr)[i - 1]);
+    if ((i == 0 && v != 0) || v < prev) SPB_FAIL(SPB_INCOMPATIBLE_FORMAT, "CSC indptr must start at 0 and be non-decreasing");
+  }
   const int64_t nnz = indptr_bits == 64 ? ((const int64_t*)indptr)[n] : (int64_t)((const int32_t*)indptr)[n];
   if (nnz < 0 || nnz >= ((int64_t)1 << 31) - 16) SPB_FAIL(SPB_INVALID_ARG, "matrix too large for the int32 ingestion path");
   const size_t m = (size_t)std::max<int64_t>(nnz, 1);

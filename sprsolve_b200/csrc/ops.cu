@@ -294,6 +294,9 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
         wave_build<T>(A, ip, cols, vals, false, op->wfwd);
       } catch (const SpbError& e) {
         fwd_status = e.status;
+      } catch (...) {  // e.g. std::bad_alloc from the host vectors: never unwind past a joinable thread
+        fwd_status = SPB_CUDA_ERROR;
+        set_last_error("Gauss-Seidel analysis failed (host allocation?)");
       }
       if (bwd_thread.joinable()) bwd_thread.join();
       if (fwd_status != SPB_OK) throw SpbError{fwd_status};
@@ -349,12 +352,10 @@ static void launch_sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T
   GsArgs<T, IP> a{bufptr<IP>(A->indptr), bufptr<int>(A->cols), bufptr<T>(A->vals), bufptr<T>(M->diag),
                   bufptr<int>(ls.level_ptr), bufptr<int>(ls.rows), (int)ls.nlevels, rhs, lo, hi, out,
                   bufptr<unsigned long long>(M->barrier), c->gate, c->gate_value};
-  static int bps = 0;
+  int bps = 0;  // per call (per device): a process may hold contexts on several GPUs
   auto kern = gs_sweep_kernel<T, IP>;
-  if (!bps) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, 0);
-    if (bps < 1) bps = 1;
-  }
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, 0);
+  if (bps < 1) bps = 1;
   // no more CTAs than the widest level can use
   int64_t widest = 1;
   for (int64_t l = 0; l < ls.nlevels; ++l)

@@ -9,9 +9,14 @@
 //   * the halo exchange is a "put": the pack kernel writes this rank's boundary x entries
 //     straight into the neighbours' halo buffers, and the SpMV kernel itself waits for the
 //     neighbours' flags right before its first boundary tile (spmv.cu).
-// Sequence numbers are monotone and every buffer is double-buffered by sequence parity; a rank can
-// only be one exchange ahead of a peer it exchanges with (it needs that peer's contribution to
-// finish its own step), so parity never collides.  The reference has no analogue (single process).
+// Sequence numbers are monotone and every buffer is double-buffered by sequence parity.  For the
+// scalar all-reduce a rank can only be one step ahead of a peer (it needs every peer's contribution
+// to finish its own step), so parity never collides.  The halo put has no such back-pressure by
+// itself -- coupling may be one-directional (a rank that only sends never waits for anybody) -- so
+// every receiver ACKNOWLEDGES: at the start of its own put s it tells each peer that its exchanges
+// < s are consumed (its SpMV s-1 is complete in stream order), and a put waits until all peers have
+// acknowledged exchange s-2, the previous user of the parity buffer it is about to overwrite.
+// The reference has no analogue (single process).
 #pragma once
 #include <stdint.h>
 
@@ -35,16 +40,17 @@ struct ScalWin {
 
 // Head of a halo window (one per partitioned matrix); the payload (2 x n_halo T, double
 // buffered) follows at kHaloHeadBytes.
-static const size_t kHaloHeadBytes = 256;
+static const size_t kHaloHeadBytes = 512;
 struct HaloHead {
   unsigned long long flags[kMaxPeers];  // flags[q] = sequence number of the last put of rank q
+  unsigned long long acks[kMaxPeers];   // acks[q] = rank q has consumed all exchanges <= this number
   unsigned long long seq;               // exchanges this rank has started
   unsigned int done;                    // CTAs of the current put that have finished
   int error;
   int npeers;                           // ranks this rank exchanges with (static after set-up)
   int peer_rank[kMaxPeers];
 };
-static_assert(sizeof(HaloHead) <= 256, "HaloHead must fit kHaloHeadBytes");
+static_assert(sizeof(HaloHead) <= kHaloHeadBytes, "HaloHead must fit kHaloHeadBytes");
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {

@@ -75,6 +75,7 @@ struct SpmvArgs {
   const unsigned short* pid;
   const int* doff;
   int dict_w;
+  int* err;  // Ctx::dev_err: set when a neighbour's halo flag never arrived
 };
 
 // x entry for local column id c.  Single GPU (HALO = false): every column is owned.  Partitioned
@@ -193,7 +194,10 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           // wait for their flags (they were sent before the neighbours' own SpMV, i.e. about one
           // interior pass ago).  Consumers only touch a tile after the full-barrier below.
           for (int j = 0; j < a.hhead->npeers; ++j)
-            if (!spin_until_ge(&a.hhead->flags[a.hhead->peer_rank[j]], hseq)) a.hhead->error = 1;
+            if (!spin_until_ge(&a.hhead->flags[a.hhead->peer_rank[j]], hseq)) {
+              a.hhead->error = 1;
+              if (a.err) *a.err = 1;
+            }
           halo_ready = true;
         }
         const int tile = a.tile_list ? a.tile_list[ti] : (int)ti;
@@ -731,14 +735,14 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
                              list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
-                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w};
+                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
       launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
       SpmvArgs<T, int32_t> a{bufptr<int32_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
                              list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
-                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w};
+                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
       launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
     }
     return grid;

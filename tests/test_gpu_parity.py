@@ -676,6 +676,70 @@ def test_results_do_not_depend_on_the_launch_plan(sp, orc, monkeypatch):
         assert np.array_equal(r[2], runs[0][2]) and np.array_equal(r[3], runs[0][3])
 
 
+def test_mv_hint_keeps_results(sp, orc):
+    """MklMat::mv_hint / mv_and_dotmv_hint (src/mkl_mat.rs:81-148: set_mv_hint + set_dotmv_hint +
+    mkl_sparse_optimize) = re-tune the launch plan with timed SpMV launches.  Like MKL's optimize it may
+    change how the product is computed, never what it computes: mul_vec, mul_vec_dot and a whole
+    preconditioned solve are bit-identical before and after, for the plain and the dictionary kernel and
+    for complex values (tests/tes_mkl_solver.rs:5-33 calls mv_and_dotmv_hint(1500) before solving)."""
+    cases = [
+        (orc.gen_convdiff27(24, 20, 18), "bicgstab"),                                # dictionary kernel
+        (orc.gen_lap3d7(30, 28, 26, shift=0.05), "minres"),                         # plain 7-point stream
+        (orc.gen_lap3d7(18, 16, 15, shift=0.5 + 0.5j, dtype=np.complex128), "csminres"),
+        (orc.gen_dirichlet2d(16)[0], "bicgstab"),                                    # tes_mkl_solver.rs: 16 x 16 grid
+    ]
+    for A, solver in cases:
+        G = to_gpu(sp, A)
+        x = _rand_vec(A.n, A.dtype)
+        rhs = orc.spmv(A, np.ones(A.n, dtype=A.dtype))
+        cls = {"bicgstab": sp.BiCGStab, "minres": sp.MinRes, "csminres": sp.CSMinRes}[solver]
+
+        def snapshot():
+            y = np.zeros(A.n, dtype=A.dtype)
+            G.mul_vec(x, y)
+            y2 = np.zeros(A.n, dtype=A.dtype)
+            d = G.mul_vec_dot(x, y2)
+            S = cls(G, A.n).record_history(1501)
+            xs = np.zeros(A.n, dtype=A.dtype)
+            it, res = S.solve(rhs, xs, 1500, 1e-8)
+            return y, y2, d, it, res, S.history.copy(), xs
+
+        before = snapshot()
+        assert np.array_equal(before[0], orc.spmv(A, x))
+        G.mv_hint(2000)
+        mid = snapshot()
+        G.mv_and_dotmv_hint(1500)
+        after = snapshot()
+        for got in (mid, after):
+            for a, b in zip(before, got):
+                assert np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b
+        info = G.plan_info()
+        assert info["consumer_threads"] % 32 == 0 and 1 <= info["stages"] <= 4
+
+
+def test_malformed_csr_is_rejected(sp):
+    """sprs::CsMat::new refuses inconsistent index arrays before any reference solver sees them; the
+    ABI does the same (SPB_INCOMPATIBLE_FORMAT) instead of letting a kernel read out of bounds."""
+    ok_ip, ok_idx, ok_v = np.array([0, 2, 3, 4]), np.array([0, 1, 1, 2], np.int32), np.ones(4)
+    sp.GpuCsrMat.new(ok_ip, ok_idx, ok_v)
+    for ip, idx in (
+        (np.array([1, 2, 3, 4]), ok_idx),                      # indptr[0] != 0
+        (np.array([0, 3, 2, 4]), ok_idx),                      # decreasing
+        (ok_ip, np.array([0, 1, 1, 3], np.int32)),             # column == ncols
+        (ok_ip, np.array([0, -1, 1, 2], np.int32)),            # negative column
+        (ok_ip.astype(np.int32), np.array([0, 1, 7, 2], np.int32)),
+    ):
+        with pytest.raises(sp.IncompatibleMatrixFormat):
+            sp.GpuCsrMat.new(ip, idx, ok_v)
+    with pytest.raises(sp.IncompatibleMatrixFormat):  # CSC column pointers
+        sp.GpuCsrMat.from_csc(np.array([0, 3, 2, 4]), ok_idx, ok_v)
+    # the context stays usable afterwards (no sticky CUDA fault)
+    G = sp.GpuCsrMat.new(ok_ip, ok_idx, ok_v)
+    y = np.zeros(3)
+    G.mul_vec(np.ones(3), y)
+    assert np.array_equal(y, [2.0, 1.0, 1.0])
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_spmv_config2_full_size_properties(sp):
     """Config C2 (256^3 7-point): size-independent properties instead of an oracle run:

@@ -75,6 +75,53 @@ def _worker(rank, world, uid, transport, out):
         x3 = np.zeros(re - rb)
         it3, rr3 = S3.solve(rhs3, x3, 500, 1e-8)
         res["minres"] = (it3, rr3, S3.history.copy(), x3.copy())
+        # ---- mv_hint on a partitioned matrix (collective): re-tunes and re-classifies the tiles, results unchanged
+        A2.mv_and_dotmv_hint(1500)
+        y = np.zeros(re - rb)
+        A2.mul_vec(xl, y)
+        res["spmv_hinted"] = y.copy()
+        S = sp.BiCGStab(A2, re - rb).record_history(600)
+        x = np.zeros(re - rb)
+        it, rr = S.precond_solve(M, rhs, x, 500, 1e-8)
+        res["bicg_hinted"] = (it, rr, S.history.copy(), x.copy())
+        # ---- the exact-dot golden case: 27-point 96^3 partitioned (tests/golden/exact_v1.npz)
+        G96 = 96
+        A96 = sp.GpuCsrMat.from_stencil(sp.STENCIL_CONVDIFF27, G96, G96, G96, params=(1.0, 0.5, 0.25), ctx=ctx)
+        nl = A96.n_local
+        o96 = np.ones(nl)
+        r96 = np.zeros(nl)
+        A96.mul_vec(o96, r96)
+        S96 = sp.BiCGStab(A96, nl).record_history(2000)
+        x96 = np.zeros(nl)
+        it96, rr96 = S96.precond_solve(sp.DiagPrecond.from_matrix(A96), r96, x96, 2000, 1e-8)
+        res["c5_96"] = (it96, rr96, S96.history.copy(), x96.copy())
+        # ---- one-directional coupling (block lower bidiagonal: rank r reads rank r-1 only, rank 0 only
+        # sends): consecutive products with a changing x and no reduction in between -- the halo put must
+        # not overwrite a parity buffer a slower neighbour still gathers from (acknowledged puts, peer.cuh)
+        nb = 4096 * world
+        lo, hi = nb // world * rank, nb // world * (rank + 1)
+        K = nb // world
+        rows = np.arange(lo, hi)
+        has = rows >= K
+        ipb = np.concatenate([[0], np.cumsum(1 + has.astype(np.int64))])
+        idxb = np.empty(ipb[-1], np.int32)
+        valb = np.empty(ipb[-1])
+        pos = ipb[:-1]
+        idxb[pos[has]] = rows[has] - K
+        valb[pos[has]] = 0.5
+        idxb[pos + has] = rows
+        valb[pos + has] = 2.0
+        AB = sp.GpuCsrMat.new(ipb, idxb, valb, shape=(nb, nb), ctx=ctx, row_range=(lo, hi))
+        import torch
+
+        dev = torch.device(f"cuda:{rank}")
+        xs = [torch.arange(lo, hi, dtype=torch.float64, device=dev) * (k + 1) + k for k in range(40)]
+        ys = [torch.empty(hi - lo, dtype=torch.float64, device=dev) for _ in range(40)]
+        torch.cuda.synchronize(dev)
+        for k in range(40):
+            AB.mul_vec_dev(xs[k].data_ptr(), ys[k].data_ptr())
+        ctx.synchronize()
+        res["onedir"] = np.stack([y.cpu().numpy() for y in ys])
         res["block"] = (rb, re)
         out.put((rank, res))
         ctx.synchronize()
@@ -140,6 +187,28 @@ def test_partitioned_parity(orc, transport):
     x1 = np.zeros(n)
     it1, rr1 = S1.precond_solve(sp.DiagPrecond.from_matrix(G1), rhs, x1, 500, 1e-8)
     assert it1 == it and rr1 == rr and np.array_equal(S1.history, hist) and np.array_equal(x1, x)
+    # mv_hint on the partitioned matrix changed nothing
+    assert np.array_equal(np.concatenate([got[r]["spmv_hinted"] for r in range(world)]), y_ref)
+    for r in range(world):
+        assert got[r]["bicg_hinted"][0] == it and np.array_equal(got[r]["bicg_hinted"][2], hist)
+    assert np.array_equal(np.concatenate([got[r]["bicg_hinted"][3] for r in range(world)]), x)
+    # ... and the exact-dot oracle bit for bit, over every iteration, on the partitioned 96^3 system
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "exact_v1.npz"))
+    it96, rr96, h96, _ = got[0]["c5_96"]
+    assert it96 == int(gold["c5_96.exact.iters"]) and rr96 == float(gold["c5_96.exact.resid"])
+    assert np.array_equal(h96, gold["c5_96.exact.hist"])
+    x96 = np.concatenate([got[r]["c5_96"][3] for r in range(world)])
+    import hashlib
+
+    assert hashlib.sha256(x96.tobytes()).hexdigest() == str(gold["c5_96.exact.x_sha256"])
+    # one-directional coupling: y_k = 2 x_k + 0.5 x_k[row - K]
+    nb = 4096 * world
+    K = nb // world
+    for k in range(40):
+        xk = np.arange(nb, dtype=np.float64) * (k + 1) + k
+        yk = 2.0 * xk
+        yk[K:] = 0.5 * xk[:-K] + 2.0 * xk[K:]
+        assert np.array_equal(np.concatenate([got[r]["onedir"][k] for r in range(world)]), yk), k
     # MINRES vs the serial oracle (well conditioned w.r.t. summation order: strict 1e-10 / +-2 %)
     A3 = orc.gen_lap3d7(G, shift=0.05)
     rhs3 = orc.spmv(A3, np.ones(n))
