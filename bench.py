@@ -21,19 +21,29 @@ e2e     : the same through the host-buffer path: each step copies rhs and x0 fro
           memory to the device, solves, and copies x back (h2d/d2h bytes per step reported); the
           caller-side zeroing of the initial guess happens before the timed region (one pinned x
           buffer per step).
-roofline: the SpMV kernel (dominant: ~80 % of an iteration's bytes), algorithmic bytes
-          nnz*12 + (n+1)*sizeof(indptr) + 2*n*8 per launch (per rank) / average launch duration
-          measured live with CUDA events around every SpMV launch of one extra profiled step.
-          `achieved` / `frac` use those ALGORITHMIC bytes (the plain CSR stream of the reference's
-          operator); when the analysis replaces the column stream by the row-pattern dictionary the
-          kernel moves fewer bytes (`stream_bytes_per_launch`, `stream_gbs`, `stream_frac` -- what
-          the HBM roofline actually bounds), so `frac` can exceed 1.
-spmv_c2 : BASELINE.json configs[1], standalone SpMV on the 3-D 7-point 256^3 matrix (N=1 only).
+roofline: the SpMV kernel (dominant: ~80 % of an iteration's bytes).  `achieved` = the ALGORITHMIC
+          bytes of the operand format the kernel consumes / the average launch
+          duration measured live with CUDA events around every SpMV launch of one extra profiled
+          step.  Plain CSR: nnz*12 + (n+1)*sizeof(indptr) + 2*n*8.  When the
+          analysis finds the column-offset dictionary (27-point matrix: 27 row patterns) the column
+          stream does not exist: nnz*8 + n*2 (pattern ids) + (n+1)*sizeof(indptr) + 2*n*8 -- these
+          are the bytes the HBM roofline bounds, so `frac` = achieved/peak stays a physical fraction.
+          `csr_equivalent_*` quote the same launch in the reference operator's CSR bytes (can exceed
+          the peak: a speed-up in format, not in bandwidth).
+spmv_c2 : BASELINE.json configs[1], standalone SpMV on the 3-D 7-point 256^3 matrix (N=1 only); x / y
+          rotate over 4 buffer pairs so no launch finds its x (134 MB, L2 evict_last) in the 126 MB L2.
+configs : (N=1 only, a few seconds) the other BASELINE configs at FULL size through the same ABI: C1
+          512^2 Jacobi-BiCGStab (single-kernel solve), C3 128^3 SGS-MINRES, C4 200^3 CSMINRES --
+          iterations/s, and whether iteration count and the whole residual history equal the committed
+          exact-dot goldens (tests/golden/exact_v1.npz) bit for bit.
+parity_check: at every N, before timing: the 27-point 96^3 system, partitioned like the workload,
+          solved to 1e-8 and compared with the exact-dot golden history bit for bit.
 cpu_baseline / --impl reference: the reference cannot be built here (Rust nightly + MKL +
           unvendored git deps, no cargo), so the CPU arm is the oracle port of its solver loop
           with OpenMP row-parallel SpMV and OpenMP vector ops (the rayon + MKL-iomp stand-in) on
           all host cores, on a bounded sample (same matrix family at a smaller grid), scaled to
-          the 512^3 unit by the row ratio.
+          the 512^3 unit by the row ratio; `extrapolation_check` times two grids (192^3, 256^3) in the
+          same run: per-row cost must agree for the scaling to be valid.
 """
 from __future__ import annotations
 
@@ -74,6 +84,45 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Multi-process runs: keep this rank (and its pinned host buffers) on the CPUs next to its GPU.
+    8 unbound processes streaming 400 MB per step through one socket is what held the e2e arm at
+    24.5 ms of copies per step at N=8 in round 1.  Returns the cpulist string or None."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/local_cpulist"
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if not part:
+                continue
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus and len(cpus) < (os.cpu_count() or 0):
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
+def exact_gold():
+    p = os.path.join(ROOT, "tests", "golden", "exact_v1.npz")
+    return np.load(p) if os.path.exists(p) else None
+
+
+def gold_match(gold, name, its, res, hist):
+    """Bit-for-bit agreement with the committed exact-dot history (a fixture, not the oracle)."""
+    if gold is None or f"{name}.exact.hist" not in gold:
+        return None
+    gh = gold[f"{name}.exact.hist"]
+    return {"case": name, "iterations": int(its), "golden_iterations": int(gold[f"{name}.exact.iters"]),
+            "residual_equal": bool(res == float(gold[f"{name}.exact.resid"])),
+            "history_bit_identical": bool(len(hist) == len(gh) and np.array_equal(np.asarray(hist), gh)), "history_len": int(len(gh))}
 
 
 class ClockSampler:
@@ -176,6 +225,11 @@ def run_reference(args):
         if time.perf_counter() - t_all > 240 and len(vals) >= 1:
             break
     v = float(np.mean(vals))
+    # validity of the row-ratio scaling: a second grid in the same run (per-row cost must agree)
+    small = cpu_bicgstab_sample(192, args.cpu_iters, args.grid)
+    extrap = {"grid_a": 192, "value_a": small["value"], "grid_b": args.cpu_grid, "value_b": v, "ratio_a_over_b": small["value"] / v,
+              "note": "both scaled to the 512^3 unit by rows; a ratio near 1 means the per-row cost does not depend on the sample size "
+                      "(both samples are far larger than the CPU caches)"}
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -194,6 +248,7 @@ def run_reference(args):
         "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")} | {"value": v},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "extrapolation_check": extrap,
     }
     emit(line)
 
@@ -219,6 +274,7 @@ def run_gpu(args):
     from sprsolve_b200 import dist as spd
 
     world, rank, local_rank = spd.env_world()
+    cpu_bind = bind_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     spd.init_process_group("nccl", device=dev)
@@ -238,6 +294,27 @@ def run_gpu(args):
         t = torch.tensor([v], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    gold = exact_gold()
+
+    # ---- parity before timing (every N): 27-point 96^3, partitioned like the workload, vs the exact-dot golden
+    parity = None
+    if not args.no_parity:
+        Ap = sp.GpuCsrMat.from_stencil(sp.STENCIL_CONVDIFF27, 96, 96, 96, params=B27, ctx=ctx)
+        npl = Ap.n_local
+        op_ = torch.ones(npl, dtype=torch.float64, device=dev)
+        rp_ = torch.empty(npl, dtype=torch.float64, device=dev)
+        xp_ = torch.zeros(npl, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        Ap.mul_vec_dev(op_.data_ptr(), rp_.data_ptr())
+        Sp = sp.BiCGStab(Ap, npl).record_history(2048)
+        itp, resp = Sp.solve_dev(rp_.data_ptr(), xp_.data_ptr(), 2000, 1e-8, precond=sp.DiagPrecond.from_matrix(Ap))
+        parity = gold_match(gold, "c5_96", itp, resp, Sp.history)
+        if parity is not None:
+            parity["ranks"] = world
+            parity["max_abs_err_vs_ones"] = max_over_ranks(float((xp_ - 1.0).abs().max().item()))
+        del Sp, Ap, op_, rp_, xp_
+        torch.cuda.empty_cache()
 
     g = args.grid
     t_setup = time.perf_counter()
@@ -354,29 +431,38 @@ def run_gpu(args):
     # one SpMV = one launch on a single GPU, two (interior + boundary rows) when partitioned
     n_products = 2 * iters + 1
     avg_ms = max_over_ranks(ms_spmv / n_products)
-    achieved = b_spmv / (avg_ms * 1e-3) / 1e9
-    # What the analysis chose for this matrix.  With the column-offset dictionary the kernel streams
-    # 8 instead of 12 bytes per non-zero, so the ALGORITHMIC figure (the bytes of the reference's CSR
-    # operator) can exceed the HBM peak; `stream_*` are the bytes the kernel
-    # moves by design, which is what the HBM roofline bounds.
+    # What the analysis chose for this matrix.  `achieved` counts the algorithmic bytes of the operand
+    # format the kernel consumes: with the column-offset dictionary there is no column
+    # stream (8 + 2/row instead of 12 bytes per non-zero), which is what the HBM roofline bounds.
+    # The same launch in the reference operator's CSR bytes is `csr_equivalent_*`.
     plan = A.plan_info()
     stream = plan["stream_bytes"]
+    achieved = stream / (avg_ms * 1e-3) / 1e9
+    csr_eq = b_spmv / (avg_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_spmv512_dict_ncu_full.json" if plan["dictionary"] else "r01_spmv512_ncu_full.json")
-    if world == 1 and g == 512 and os.path.exists(tp):
-        traffic = float(json.load(open(tp))["traffic_bytes_per_launch"])
-        traffic_src = f"profiles/{os.path.basename(tp)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, same workload)"
+    if world == 1 and g == 512:
+        stem = "spmv512_dict_ncu_full.json" if plan["dictionary"] else "spmv512_ncu_full.json"
+        for rnd in ("r02", "r01"):
+            tp = os.path.join(ROOT, "profiles", f"{rnd}_{stem}")
+            if os.path.exists(tp):
+                meta = json.load(open(tp))
+                traffic = float(meta["traffic_bytes_per_launch"])
+                traffic_src = (f"profiles/{os.path.basename(tp)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, same workload"
+                               + (f", captured at commit {meta['commit']}" if "commit" in meta else "") + ")")
+                break
     roofline = {
         "bound": "hbm", "kernel": "spmv_tma_kernel<double> (CSR SpMV, 27-pt, this rank's rows)", "achieved": achieved, "peak": peak,
         "unit": "GB/s (per GPU)", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "frac_basis": "algorithmic bytes of the operand format the kernel consumes (bytes_per_launch)",
         "format": (f"CSR values + 16-bit row-pattern ids ({plan['patterns']} column-offset patterns found by the analysis)"
                    if plan["dictionary"] else "CSR values + int32 column indices"),
-        "stream_bytes_per_launch": stream, "stream_gbs": stream / (avg_ms * 1e-3) / 1e9, "stream_frac": stream / (avg_ms * 1e-3) / 1e9 / peak,
+        "csr_equivalent_bytes_per_launch": b_spmv, "csr_equivalent_gbs": csr_eq, "csr_equivalent_frac": csr_eq / peak,
         "plan": {k: plan[k] for k in ("consumer_threads", "stages", "tile_nnz", "ctas_per_sm")},
-        "bytes_per_launch": b_spmv, "avg_launch_ms": avg_ms, "launches_timed": n_spmv, "products_timed": n_products,
+        "bytes_per_launch": stream, "avg_launch_ms": avg_ms, "launches_timed": n_spmv, "products_timed": n_products,
         "step_share": {"spmv_ms": ms_spmv, "vector_ms": ms_vec, "scalar_ms": ms_sc, "spmv_launches": n_spmv, "vector_launches": n_vec, "scalar_launches": n_sc},
-        "iteration_bytes_model": 2 * b_spmv + 21 * n_loc * 8,
-        "iteration_gbs_device": (2 * b_spmv + 21 * n_loc * 8) * value / 1e9,
+        "iteration_bytes_model": 2 * stream + 21 * n_loc * 8,
+        "iteration_gbs_device": (2 * stream + 21 * n_loc * 8) * value / 1e9,
+        "iteration_frac_of_peak": (2 * stream + 21 * n_loc * 8) * value / 1e9 / peak,
     }
 
     # ---- BASELINE.json configs[1]: standalone SpMV on 256^3 7-point (N=1 only)
@@ -388,29 +474,120 @@ def run_gpu(args):
         A2 = sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, n1, n1, n1, params=(0.0,), ctx=ctx)
         n2 = n1**3
         k = torch.arange(n2, device=dev)
-        x2 = 1.0 + (k % 17).double() / 17.0
-        y2 = torch.empty(n2, dtype=torch.float64, device=dev)
-        for _ in range(5):
-            A2.mul_vec_dev(x2.data_ptr(), y2.data_ptr())
+        nrot = 4  # x / y pairs: a launch never finds its own x (evict_last) left in L2 by the previous one
+        xs2 = [1.0 + ((k + 3 * j) % 17).double() / 17.0 for j in range(nrot)]
+        ys2 = [torch.empty(n2, dtype=torch.float64, device=dev) for _ in range(nrot)]
+        del k
+        for j in range(5):
+            A2.mul_vec_dev(xs2[j % nrot].data_ptr(), ys2[j % nrot].data_ptr())
         torch.cuda.synchronize()
-        reps = 50
+        reps = 48
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
-            A2.mul_vec_dev(x2.data_ptr(), y2.data_ptr())
+        for j in range(reps):
+            A2.mul_vec_dev(xs2[j % nrot].data_ptr(), ys2[j % nrot].data_ptr())
         e1.record()
         torch.cuda.synchronize()
         ms2 = e0.elapsed_time(e1) / reps
+        e0.record()
+        for j in range(reps):
+            A2.mul_vec_dev(xs2[0].data_ptr(), ys2[0].data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms2_same = e0.elapsed_time(e1) / reps
         b2 = spmv_bytes(n2, A2.nnz, 4)
         spmv_c2 = {"workload": "BASELINE.json configs[1]: CSR SpMV f64, 3-D 7-point 256^3", "ms": ms2, "bytes": b2,
                    "gbs": b2 / (ms2 * 1e-3) / 1e9, "frac_of_peak": b2 / (ms2 * 1e-3) / 1e9 / peak, "launches": reps,
-                   "note": "1.74 GB per launch > 126 MB L2, back-to-back launches"}
+                   "note": f"1.74 GB per launch > 126 MB L2; x / y rotate over {nrot} buffer pairs (no x survives in L2 between launches)",
+                   "same_buffer_ms": ms2_same, "same_buffer_gbs": b2 / (ms2_same * 1e-3) / 1e9}
+        del A2, xs2, ys2
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs at full size (N=1 only; seconds): it/s + bit-for-bit parity flags
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+
+        def solve_cfg(name, G, cls, Mc, ones_value, cplx, reps):
+            nloc = G.n_local
+            tdt = torch.complex128 if cplx else torch.float64
+            o_ = torch.full((nloc,), ones_value, dtype=tdt, device=dev)
+            r_ = torch.empty(nloc, dtype=tdt, device=dev)
+            x_ = torch.zeros(nloc, dtype=tdt, device=dev)
+            torch.cuda.synchronize()
+            G.mul_vec_dev(o_.data_ptr(), r_.data_ptr())
+            Sc = cls(G, nloc).record_history(16384)
+            best = None
+            for _ in range(reps + 1):
+                x_.zero_()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = ctx.launch_count
+                a0.record()
+                it_, res_ = Sc.solve_dev(r_.data_ptr(), x_.data_ptr(), 10000, 1e-8, precond=Mc)
+                a1.record()
+                torch.cuda.synchronize()
+                ms_ = a0.elapsed_time(a1)
+                best = ms_ if best is None else min(best, ms_)
+                nl_ = ctx.launch_count - l0
+            return {"iterations": it_, "rel_residual": res_, "solve_ms": best, "iters_per_s": it_ / (best * 1e-3), "us_per_iter": 1e3 * best / max(it_, 1),
+                    "launches_per_solve": nl_, "parity": gold_match(gold, name, it_, res_, Sc.history)}
+
+        try:
+            # C1: the reference's Dirichlet matrix (src/main.rs:53-88) generated on the device; rhs = i + j on the border
+            g1 = 512
+            A1 = sp.GpuCsrMat.from_stencil(sp.STENCIL_DIRICHLET2D, g1, g1, 1, ctx=ctx)
+            ii, jj = np.meshgrid(np.arange(g1), np.arange(g1), indexing="ij")
+            border = (ii == 0) | (ii == g1 - 1) | (jj == 0) | (jj == g1 - 1)
+            rhs1 = torch.from_numpy(np.where(border, (ii + jj).astype(np.float64), 0.0).ravel()).to(dev)
+            x1 = torch.zeros(g1 * g1, dtype=torch.float64, device=dev)
+            M1 = sp.DiagPrecond.from_matrix(A1)
+            S1 = sp.BiCGStab(A1, g1 * g1).record_history(16384)
+            best, nl1 = None, 0
+            for _ in range(4):
+                x1.zero_()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                l0 = ctx.launch_count
+                a0.record()
+                it1, res1 = S1.solve_dev(rhs1.data_ptr(), x1.data_ptr(), 10000, 1e-8, precond=M1)
+                a1.record()
+                torch.cuda.synchronize()
+                nl1 = ctx.launch_count - l0
+                ms1 = a0.elapsed_time(a1)
+                best = ms1 if best is None else min(best, ms1)
+            configs["c1"] = {"workload": "BASELINE.json configs[0]: Jacobi-BiCGStab f64, reference 2-D 5-point Dirichlet matrix 512^2, rtol 1e-8",
+                             "iterations": it1, "rel_residual": res1, "solve_ms": best, "iters_per_s": it1 / (best * 1e-3),
+                             "us_per_iter": 1e3 * best / max(it1, 1), "launches_per_solve": nl1,
+                             "path": "single cooperative kernel (L2-resident system)" if nl1 <= 2 else "multi-kernel loop",
+                             "parity": gold_match(gold, "c1_512", it1, res1, S1.history)}
+            del S1, M1, A1, rhs1, x1
+            A3 = sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, 128, 128, 128, params=(0.05,), ctx=ctx)
+            t0 = time.perf_counter()
+            M3 = sp.GaussSeidelPrecond(A3, symmetric=True)
+            gs_setup = time.perf_counter() - t0
+            configs["c3"] = {"workload": "BASELINE.json configs[2]: MINRES f64, shifted 7-point 128^3, symmetric Gauss-Seidel preconditioner, rtol 1e-8",
+                             "gs_analysis_seconds": gs_setup} | solve_cfg("c3_128", A3, sp.MinRes, M3, 1.0, False, 1)
+            configs["c3_plain"] = {"workload": "the same system without preconditioner"} | solve_cfg("c3_128_plain", A3, sp.MinRes, None, 1.0, False, 2)
+            del M3, A3
+            torch.cuda.empty_cache()
+            A4 = sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, 200, 200, 200, params=(0.5, 0.5), dtype=np.complex128, ctx=ctx)
+            configs["c4"] = {"workload": "BASELINE.json configs[3]: CSMINRES complex128, complex-symmetric Helmholtz 7-point 200^3, rtol 1e-8"} | solve_cfg(
+                "c4_200", A4, sp.CSMinRes, None, 1 + 1j, True, 2)
+            del A4
+            torch.cuda.empty_cache()
+        except Exception as e:  # the headline line must survive a failure in the extras
+            configs["error"] = f"{type(e).__name__}: {e}"
+
 
     # ---- CPU baseline on rank 0 at N=1
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
-        cpu = cpu_bicgstab_sample(args.cpu_grid, args.cpu_iters, g)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_s = cpu_bicgstab_sample(args.cpu_grid, args.cpu_iters, g)
+        cpu = {k: cpu_s[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        small = cpu_bicgstab_sample(192, args.cpu_iters, g)
+        cpu["extrapolation_check"] = {"grid_a": 192, "value_a": small["value"], "grid_b": args.cpu_grid, "value_b": cpu_s["value"],
+                                      "ratio_a_over_b": small["value"] / cpu_s["value"]}
 
     if rank == 0:
         line = {
@@ -421,7 +598,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n_loc * 8 * world, "d2h_bytes_per_step": n_loc * 8 * world,
                     "ms_per_step": ms_e2e / args.steps, "api": "BiCGStab.precond_solve on pinned host slices (spb_solver_solve)",
                     "max_abs_diff_vs_device_resident_step": e2e_check},
-            "gpu_launches": launches, "clocks": clocks, "full_solve": full, "spmv_c2": spmv_c2, "setup_seconds": setup_s,
+            "gpu_launches": launches, "clocks": clocks, "full_solve": full, "spmv_c2": spmv_c2, "configs": configs,
+            "parity_check": parity, "cpu_binding": cpu_bind, "setup_seconds": setup_s,
         }
         emit(line)
     if world > 1:
@@ -445,6 +623,8 @@ def main():
     ap.add_argument("--no-full-solve", action="store_true")
     ap.add_argument("--no-c2", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C1 / C3 / C4 extras (N=1)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the exact-dot golden check before timing")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3

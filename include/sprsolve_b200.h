@@ -7,7 +7,9 @@
  * `impl MatVecMul<T> for GpuCsrMat<T>`) is shown in INTEGRATION.md and shipped as source in rust/.
  *
  * Conventions
- *   - dtype: SPB_F64 = f64, SPB_C128 = num_complex::Complex64 (interleaved re,im doubles).
+ *   - dtype: SPB_F64 = f64, SPB_C128 = num_complex::Complex64 (interleaved re,im doubles),
+ *     SPB_F32 = f32, SPB_C64 = num_complex::Complex32 (interleaved re,im floats).  Scalars that cross
+ *     the ABI (a, b, dot results, tol, resid) are always doubles; for the f32 types they hold floats.
  *   - Column indices are int32 (MklMat: `Vec<i32>`, src/mkl_mat.rs:17-18); row pointers int32 or int64.
  *   - Every function returns an spb_status.  Values 1..5 map 1:1 onto `SolverError`
  *     (src/error.rs:7-22).  Nothing panics or throws across the ABI; where the reference panics
@@ -47,7 +49,9 @@ typedef enum {
   SPB_NO_DEVICE = 103
 } spb_status;
 
-typedef enum { SPB_F64 = 0, SPB_C128 = 1 } spb_dtype;
+/* cauchy::Scalar is implemented for f32, f64, Complex32, Complex64; MklMat dispatches s/d/c/z
+ * (src/mkl_mat.rs:68-71,198-201,220).  The f32 types compute every T::Real quantity in float. */
+typedef enum { SPB_F64 = 0, SPB_C128 = 1, SPB_F32 = 2, SPB_C64 = 3 } spb_dtype;
 
 /* Synthetic on-device matrix generators.  params: see each kind. */
 typedef enum {
@@ -116,8 +120,9 @@ int spb_csr_create_from_triplets(spb_ctx* ctx, int dtype, int64_t nrows, int64_t
 int spb_csr_read_matrix_market(spb_ctx* ctx, int dtype, const char* path, spb_op** out);
 /* MklMat::mv_hint / mv_and_dotmv_hint (src/mkl_mat.rs:81-148), i.e. mkl_sparse_set_mv_hint +
  * mkl_sparse_optimize: time a handful of launch plans with real SpMV launches on this matrix and
- * keep the fastest.  Optional: spb_csr_create already picks a static plan.  The plan fixes the
- * summation order of the fused dot products, so call it before the first solve if at all.
+ * keep the fastest.  Optional: spb_csr_create already picks a static plan.  Results never depend on
+ * the plan (every row is folded in CSR order; the fused dot products are exactly rounded,
+ * csrc/reduce.cuh), so it may be called at any time.
  * Collective when the matrix is partitioned (every rank must call it). */
 int spb_csr_mv_hint(spb_op* mat, int ncalls);
 int spb_csr_mv_and_dotmv_hint(spb_op* mat, int ncalls);
@@ -146,7 +151,8 @@ int spb_op_mul_vec_dot_dev(spb_op* op, const void* d_in, void* d_out, double out
 
 /* ---- preconditioners -------------------------------------------------------------------------- */
 /* DiagPrecond::new(diag) (src/precond.rs:20-29): stores 1/diag.  diag_dtype may be SPB_F64 while
- * dtype is SPB_C128 (DiagPrecond<Complex64,f64>, tests/test_complex_solve.rs:44). */
+ * dtype is SPB_C128 (DiagPrecond<Complex64,f64>, tests/test_complex_solve.rs:44); likewise SPB_F32
+ * for SPB_C64. */
 int spb_diag_precond_create(spb_ctx* ctx, int dtype, int diag_dtype, const void* diag, int64_t n,
                             spb_op** out);
 /* Same, taking diag(A) on the device (for generated matrices too large to stage on the host). */

@@ -24,7 +24,7 @@ NCCL_ERROR = 101
 INVALID_ARG = 102
 NO_DEVICE = 103
 
-F64, C128 = 0, 1
+F64, C128, F32, C64 = 0, 1, 2, 3
 STENCIL_DIRICHLET2D, STENCIL_LAP3D7, STENCIL_CONVDIFF27 = 0, 1, 2
 GS_FORWARD, GS_SYMMETRIC = 0, 1
 

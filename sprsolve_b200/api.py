@@ -13,7 +13,7 @@ Rust crate, so the parity tests read like the reference's own tests:
     SolverError::*                src/error.rs     SolverError subclasses
     vecalg::{dot,conj_dot,...}    src/vecalg.rs    sprsolve_b200.vecalg.*
 
-Vectors are numpy arrays (float64 / complex128) standing in for `&[T]` / `&mut [T]`; `x` is
+Vectors are numpy arrays (float64 / complex128 / float32 / complex64) standing in for `&[T]` / `&mut [T]`; `x` is
 updated in place like the reference's `&mut [T]`.  Everything computes on the GPU through the
 C ABI; nothing here does arithmetic.
 """
@@ -96,17 +96,27 @@ def _check(status: int):
         _raise(status)
 
 
+_CODES = {np.dtype(np.float64): F.F64, np.dtype(np.complex128): F.C128, np.dtype(np.float32): F.F32, np.dtype(np.complex64): F.C64}
+SCALAR_TYPES = (np.float64, np.complex128, np.float32, np.complex64)  # cauchy::Scalar: f64, Complex64, f32, Complex32
+
+
 def _dtype_code(dtype) -> int:
     k = np.dtype(dtype)
-    if k == np.float64:
-        return F.F64
-    if k == np.complex128:
-        return F.C128
-    raise TypeError(f"unsupported scalar type {k} (f64 and Complex<f64> are implemented)")
+    if k in _CODES:
+        return _CODES[k]
+    raise TypeError(f"unsupported scalar type {k} (f32, f64, Complex<f32>, Complex<f64> are implemented)")
 
 
 def _np_dtype(code: int):
-    return np.float64 if code == F.F64 else np.complex128
+    return {v: k for k, v in _CODES.items()}[code].type
+
+
+def _as_scalar_array(data):
+    """Contiguous array of one of the four scalar types; anything else is promoted to f64 / Complex64."""
+    data = np.ascontiguousarray(data)
+    if data.dtype not in _CODES:
+        data = data.astype(np.complex128 if np.iscomplexobj(data) else np.float64)
+    return data
 
 
 def _ptr(a):
@@ -265,9 +275,7 @@ class GpuCsrMat(MatVecMul):
         row_range=(begin, end): this rank's row block of a partitioned matrix (indptr local,
         indices global)."""
         ctx = ctx or default_context()
-        data = np.ascontiguousarray(data)
-        if data.dtype not in (np.float64, np.complex128):
-            data = data.astype(np.complex128 if np.iscomplexobj(data) else np.float64)
+        data = _as_scalar_array(data)
         indices = np.ascontiguousarray(indices, dtype=np.int32)
         indptr = np.ascontiguousarray(indptr)
         if indptr.dtype == np.int32:
@@ -288,10 +296,7 @@ class GpuCsrMat(MatVecMul):
 
     @staticmethod
     def _values(data):
-        data = np.ascontiguousarray(data)
-        if data.dtype not in (np.float64, np.complex128):
-            data = data.astype(np.complex128 if np.iscomplexobj(data) else np.float64)
-        return data
+        return _as_scalar_array(data)
 
     @classmethod
     def from_csc(cls, indptr, row_indices, data, shape=None, ctx: Context | None = None):
@@ -391,10 +396,15 @@ class DiagPrecond(MatVecMul):
     def new(cls, diag, dtype=None, ctx: Context | None = None):
         """DiagPrecond::new(diag): stores 1/diag (src/precond.rs:20-29)."""
         ctx = ctx or default_context()
-        diag = np.ascontiguousarray(diag)
-        ddt = np.complex128 if np.iscomplexobj(diag) else np.float64
-        diag = diag.astype(ddt)
+        diag = _as_scalar_array(diag)
+        ddt = diag.dtype.type
         dtype = np.dtype(dtype or ddt).type
+        # V = T or V = T::Real: bring the diagonal to the precision of the system
+        single = np.dtype(dtype).itemsize in (4, 8) and np.dtype(dtype) in (np.dtype(np.float32), np.dtype(np.complex64))
+        want = (np.complex64 if single else np.complex128) if np.iscomplexobj(diag) else (np.float32 if single else np.float64)
+        if ddt != want:
+            diag = diag.astype(want)
+            ddt = want
         h = C.c_void_p()
         _check(F.lib().spb_diag_precond_create(ctx._h, _dtype_code(dtype), _dtype_code(ddt), _ptr(diag), diag.size, C.byref(h)))
         return cls(h, ctx, dtype)

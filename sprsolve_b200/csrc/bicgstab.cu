@@ -25,7 +25,7 @@ template <typename T>
 struct BicgState {
   StateHead h;
   T rho, rho_old, alpha, w, beta, c_pv, nalpha, nw;
-  double rhs_norm, tol2, r0_norm_tol, r_norm, tol;
+  real_t<T> rhs_norm, tol2, r0_norm_tol, r_norm, tol;  // T::Real quantities (f32 solvers: float, as in the reference)
 };
 
 __device__ __forceinline__ void hist_put(StateHead& h, double* hist, long long cap, long long k, double v) {
@@ -36,13 +36,14 @@ __device__ __forceinline__ void hist_put(StateHead& h, double* hist, long long c
 // ---------------------------------------------------------------- scalar kernels (1 thread)
 template <typename T>
 __device__ __forceinline__ void bicg_s_rhs_body(BicgState<T>* st, const scal2* red) {
-  const double rhs_norm = sqrt(red[0].re);  // norm2(rhs), :225
+  using R = real_t<T>;
+  const R rhs_norm = sqrt_r((R)red[0].re);  // norm2(rhs), :225
   st->rhs_norm = rhs_norm;
   st->tol2 = st->tol * rhs_norm;            // :231
-  if (rhs_norm <= SPB_EPS) {                // :226-230
+  if (rhs_norm <= eps_of<T>()) {            // :226-230
     st->h.status = DS_ZERO_RHS;
     st->h.res_iters = 0;
-    st->h.res_resid = rhs_norm;
+    st->h.res_resid = (double)rhs_norm;
   }
 }
 
@@ -55,21 +56,22 @@ __global__ void bicg_s_rhs(BicgState<T>* st, const scal2* red) {
 template <typename T>
 __device__ __forceinline__ void bicg_s_init_body(BicgState<T>* st, const scal2* red, double* hist, long long cap, int restart) {
   if (restart ? st->h.status != DS_NEED_RESTART : st->h.status != DS_RUNNING) return;
-  const double rn = sqrt(red[0].re);
+  using R = real_t<T>;
+  const R rn = sqrt_r((R)red[0].re);
   if (!restart) {
-    hist_put(st->h, hist, cap, 0, rn / st->rhs_norm);
+    hist_put(st->h, hist, cap, 0, (double)(rn / st->rhs_norm));
     if (rn <= st->tol2) {  // :252-254
       st->h.status = DS_OK;
       st->h.res_iters = 0;
-      st->h.res_resid = rn / st->rhs_norm;
+      st->h.res_resid = (double)(rn / st->rhs_norm);
       return;
     }
-    double t = rn * SPB_EPS;  // :255-256
+    R t = rn * eps_of<T>();  // :255-256
     st->r0_norm_tol = t * t;
     st->rho = from_real<T>(rn * rn);  // :259
   } else {
-    st->rho = from_real<T>(rn * rn);                              // :316
-    st->r0_norm_tol = re_of(st->rho) * SPB_EPS * SPB_EPS;         // :317
+    st->rho = from_real<T>(rn * rn);                                        // :316
+    st->r0_norm_tol = re_of(st->rho) * eps_of<T>() * eps_of<T>();         // :317
     const T beta = mul(divi(st->rho, st->rho_old), divi(st->alpha, st->w));  // :319
     st->beta = beta;
     st->c_pv = mul(neg(beta), st->w);
@@ -86,13 +88,14 @@ template <typename T>
 __device__ __forceinline__ void bicg_s1_body(BicgState<T>* st, const scal2* red, double* hist, long long cap) {
   if (st->h.status != DS_RUNNING) return;
   const long long its = ++st->h.its;
-  const double r_norm = sqrt(red[0].re);  // :296
+  using R = real_t<T>;
+  const R r_norm = sqrt_r((R)red[0].re);  // :296
   st->r_norm = r_norm;
-  hist_put(st->h, hist, cap, its, r_norm / st->rhs_norm);
+  hist_put(st->h, hist, cap, its, (double)(r_norm / st->rhs_norm));
   if (r_norm <= st->tol2) {  // :297-299
     st->h.status = DS_OK;
     st->h.res_iters = its;
-    st->h.res_resid = r_norm / st->rhs_norm;
+    st->h.res_resid = (double)(r_norm / st->rhs_norm);
     return;
   }
   st->rho_old = st->rho;             // :300
@@ -115,7 +118,7 @@ template <typename T>
 __device__ __forceinline__ void bicg_s2_body(BicgState<T>* st, const scal2* red, int first) {
   if (st->h.status != DS_RUNNING) return;
   const T tmp = from_scal2<T>(red[0]);  // conj_dot(r0, v), :332
-  if (!first && abs_of(tmp) <= 0.0) {   // :333-336 (the unrolled first iteration has no test, :266)
+  if (!first && abs_of(tmp) <= (real_t<T>)0) {   // :333-336 (the unrolled first iteration has no test, :266)
     st->h.status = DS_BREAKDOWN;
     st->h.res_iters = st->h.its;
     return;
@@ -136,7 +139,7 @@ template <typename T>
 __device__ __forceinline__ void bicg_s3_body(BicgState<T>* st, const scal2* red) {
   if (st->h.status != DS_RUNNING) return;
   const T tt = from_scal2<T>(red[0]);  // conj_dot(t, t), :347
-  st->w = re_of(tt) > 0.0 ? divi(from_scal2<T>(red[1]), tt) : zero_of<T>();  // :348-352
+  st->w = re_of(tt) > (real_t<T>)0 ? divi(from_scal2<T>(red[1]), tt) : zero_of<T>();  // :348-352
   st->nw = neg(st->w);
 }
 // fused into the kernel that finishes <t, t>, <t, r>
@@ -241,6 +244,7 @@ struct FusedArgs {
   double* hist;
   long long cap, max_iter;
   double tol;
+  long long* stats;  // optional (SPB_FUSED_STATS=1): clocks of CTA 0 per phase, see the lap() calls
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
@@ -259,84 +263,132 @@ __device__ __forceinline__ cplx ld_ro(const cplx* p) {
   const double2 v = __ldg(reinterpret_cast<const double2*>(p));
   return cplx{v.x, v.y};
 }
-__device__ __forceinline__ Acc<double> ld_l2(const Acc<double>* p) {
+__device__ __forceinline__ float ld_l2(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ cplxf ld_l2(const cplxf* p) {
+  const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  return cplxf{v.x, v.y};
+}
+__device__ __forceinline__ float ld_ro(const float* p) { return __ldg(p); }
+__device__ __forceinline__ cplxf ld_ro(const cplxf* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return cplxf{v.x, v.y};
+}
+__device__ __forceinline__ AccR ld_l2(const AccR* p) {
   const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-  return Acc<double>{v.x, v.y};
+  return AccR{v.x, v.y};
 }
-__device__ __forceinline__ Acc<cplx> ld_l2(const Acc<cplx>* p) {
+__device__ __forceinline__ AccC ld_l2(const AccC* p) {
   const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-  return Acc<cplx>{a.x, a.y, b.x, b.y};
+  return AccC{a.x, a.y, b.x, b.y};
 }
-__device__ __forceinline__ scal2 acc_round(const Acc<double>& a) { return scal2{a.hi + a.lo, 0.0}; }
-__device__ __forceinline__ scal2 acc_round(const Acc<cplx>& a) { return scal2{a.rh + a.rl, a.ih + a.il}; }
+template <typename T>
+__device__ __forceinline__ scal2 acc_round(const AccR& a) {
+  return scal2{round_to_real<T>(a.hi + a.lo), 0.0};
+}
+template <typename T>
+__device__ __forceinline__ scal2 acc_round(const AccC& a) {
+  return scal2{round_to_real<T>(a.rh + a.rl), round_to_real<T>(a.ih + a.il)};
+}
 
 // One CSR row folded sequentially in CSR order (src/mat.rs:100-105); matrix through the read-only path
-// (constant for the whole kernel, L1-resident after the first iteration), x at L2.
+// (constant for the whole kernel, L1-resident after the first iteration), x at L2.  Gathers are issued
+// 8 per batch: a row of <= 8 entries costs one L2 round trip.
 template <typename T>
 __device__ __forceinline__ T fused_row(const FusedArgs<T>& a, int i, const T* src) {
   const int p0 = __ldg(a.indptr + i), p1 = __ldg(a.indptr + i + 1);
   T acc = zero_of<T>();
-  for (int k = p0; k < p1; k += 4) {
-    int c[4];
-    T m[4], xv[4];
+  for (int k = p0; k < p1; k += 8) {
+    int c[8];
+    T m[8], xv[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < 8; ++j) {
       const int kk = min(k + j, p1 - 1);
       c[j] = __ldg(a.cols + kk);
       m[j] = ld_ro(a.vals + kk);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) xv[j] = ld_l2(src + c[j]);
+    for (int j = 0; j < 8; ++j) xv[j] = ld_l2(src + c[j]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 8; ++j)
       if (k + j < p1) acc = add(acc, mul(xv[j], m[j]));
   }
   return acc;
 }
 
+__device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 template <typename T, typename V, bool PC, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T> a) {
+  constexpr int NW = BLOCK / 32;
   __shared__ BicgState<T> S;
-  __shared__ scal2 red[2];
-  __shared__ Acc<T> scratch[32];
-  const int tid = threadIdx.x;
+  __shared__ Acc<T> wsum[2][NW];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int gtid = blockIdx.x * BLOCK + tid, nth = gridDim.x * BLOCK, n = a.n;
   const V* dinv = static_cast<const V*>(a.dinv);
   double* hist = blockIdx.x == 0 ? a.hist : nullptr;  // one writer
   unsigned long long target = 0;
   int rp = 0;  // reduction points cycle through three partial buffers (a buffer is re-written two barriers later)
+  scal2 red[2];
+  long long t_last = a.stats ? clock64() : 0;
+  auto lap = [&](int k) {  // diagnostics: phase clocks of CTA 0
+    if (a.stats && blockIdx.x == 0 && tid == 0) {
+      const long long now = clock64();
+      a.stats[k] += now - t_last;
+      t_last = now;
+    }
+  };
 
+  // Grid barrier: a release-add without return value (the arriving thread does not wait for the round
+  // trip) and an acquire spin by one thread per CTA; __syncthreads on both sides extends the ordering to
+  // the whole CTA.
   auto grid_sync = [&]() {
     __syncthreads();
     if (tid == 0) {
       target += gridDim.x;
-      __threadfence();
-      atomicAdd(a.bar, 1ULL);
+      red_release_gpu_add(a.bar, 1ULL);
       while (ld_acquire_gpu_u64(a.bar) < target) {
       }
-      __threadfence();
     }
     __syncthreads();
   };
-  // this CTA's partials of a reduction point; after the barrier every CTA sums all of them in the same
-  // fixed order and rounds once -> red[0], red[1] (identical in every CTA)
-  auto reduce = [&](Acc<T> e0, Acc<T> e1) {
-    e0 = block_sum(e0, scratch);
-    e1 = block_sum(e1, scratch);
-    Acc<T>* pb = a.parts + (size_t)rp * 2 * gridDim.x;
-    if (tid == 0) {
-      pb[2 * blockIdx.x] = e0;
-      pb[2 * blockIdx.x + 1] = e1;
+  // A reduction point.  Block partial: warp shuffles, one shared-memory hop, the first warp folds the
+  // warps; after the barrier EVERY WARP of every CTA sums all CTA partials itself (fixed order, both
+  // slots interleaved) and rounds once: red[] lands in registers, identical everywhere.
+  auto reduce = [&](Acc<T> e0, Acc<T> e1, bool two) {
+    e0 = warp_sum(e0);
+    if (two) e1 = warp_sum(e1);
+    if (lane == 0) {
+      wsum[0][wid] = e0;
+      wsum[1][wid] = e1;
     }
-    grid_sync();
-    for (int slot = 0; slot < 2; ++slot) {
-      Acc<T> acc = zero_of<Acc<T>>();
-      for (int i = tid; i < (int)gridDim.x; i += BLOCK) acc = add(acc, ld_l2(pb + 2 * i + slot));
-      acc = block_sum(acc, scratch);
-      if (tid == 0) red[slot] = acc_round(acc);
-    }
-    rp = rp == 2 ? 0 : rp + 1;
     __syncthreads();
+    Acc<T>* pb = a.parts + (size_t)rp * 2 * gridDim.x;
+    if (wid == 0) {
+      Acc<T> b0 = lane < NW ? wsum[0][lane] : zero_of<Acc<T>>();
+      Acc<T> b1 = lane < NW ? wsum[1][lane] : zero_of<Acc<T>>();
+      b0 = warp_sum(b0);
+      if (two) b1 = warp_sum(b1);
+      if (lane == 0) {
+        pb[2 * blockIdx.x] = b0;
+        pb[2 * blockIdx.x + 1] = b1;
+      }
+    }
+    lap(5);  // block partial
+    grid_sync();
+    lap(6);  // barrier of a reduction point
+    Acc<T> g0 = zero_of<Acc<T>>(), g1 = zero_of<Acc<T>>();
+    for (int i = lane; i < (int)gridDim.x; i += 32) {
+      g0 = add(g0, ld_l2(pb + 2 * i));
+      if (two) g1 = add(g1, ld_l2(pb + 2 * i + 1));
+    }
+    g0 = warp_sum(g0);
+    if (two) g1 = warp_sum(g1);
+    red[0] = acc_round<T>(g0);
+    red[1] = acc_round<T>(g1);  // (valid in lane 0 of every warp; thread 0 is the only consumer)
+    rp = rp == 2 ? 0 : rp + 1;
+    lap(7);  // sum of the CTA partials
   };
   // r = A x - rhs ; r0 = r ; ||r||^2   (:243-251, and the restart :305-316)
   auto residual = [&](int restart) {
@@ -348,7 +400,7 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
       a.r0[i] = ri;
       acc_sq(e0, ri);
     }
-    reduce(e0, zero_of<Acc<T>>());
+    reduce(e0, zero_of<Acc<T>>(), false);
     if (tid == 0) bicg_s_init_body(&S, red, hist, a.cap, restart);
     __syncthreads();
   };
@@ -368,7 +420,9 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
         if (PC) a.y[i] = mul_diag(pi, dinv[i]);
       }
     }
+    lap(0);  // K1
     grid_sync();  // y complete
+    lap(8);  // plain barrier
     {  // v = A y, <r0, v>
       Acc<T> e0 = zero_of<Acc<T>>();
       for (int i = gtid; i < n; i += nth) {
@@ -376,10 +430,12 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
         a.v[i] = vi;
         acc_prod(e0, conj_of(a.r0[i]), vi);
       }
-      reduce(e0, zero_of<Acc<T>>());
+      lap(1);  // SpMV 1
+      reduce(e0, zero_of<Acc<T>>(), false);
     }
     if (tid == 0) bicg_s2_body(&S, red, first ? 1 : 0);
     __syncthreads();
+    lap(9);  // scalar step
     if (S.h.status != DS_RUNNING) return false;
     {  // K2
       const T nalpha = S.nalpha;
@@ -389,7 +445,9 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
         if (PC) a.z[i] = mul_diag(ri, dinv[i]);
       }
     }
+    lap(2);  // K2
     grid_sync();  // z complete
+    lap(8);
     {  // t = A z, <t,t>, <t,r>
       Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
       for (int i = gtid; i < n; i += nth) {
@@ -399,10 +457,12 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
         acc_prod(e0, cy, ti);
         acc_prod(e1, cy, a.r[i]);
       }
-      reduce(e0, e1);
+      lap(3);  // SpMV 2
+      reduce(e0, e1, true);
     }
     if (tid == 0) bicg_s3_body(&S, red);
     __syncthreads();
+    lap(9);
     {  // K3 + the partials of the next iteration's test
       Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
       const T nalpha = S.nalpha, nw = S.nw;
@@ -416,7 +476,8 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
         acc_sq(e0, ri);
         acc_prod(e1, conj_of(a.r0[i]), ri);
       }
-      reduce(e0, e1);
+      lap(4);  // K3
+      reduce(e0, e1, true);
     }
     return true;
   };
@@ -424,13 +485,13 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
   if (tid == 0) {
     memset(&S, 0, sizeof(S));
     S.h.status = DS_RUNNING;
-    S.tol = a.tol;
+    S.tol = (real_t<T>)a.tol;
   }
   __syncthreads();
   {  // ||b||  (:225-231)
     Acc<T> e0 = zero_of<Acc<T>>();
     for (int i = gtid; i < n; i += nth) acc_sq(e0, a.rhs[i]);
-    reduce(e0, zero_of<Acc<T>>());
+    reduce(e0, zero_of<Acc<T>>(), false);
     if (tid == 0) bicg_s_rhs_body(&S, red);
     __syncthreads();
   }
@@ -442,6 +503,7 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
       for (long long k = 1; k < a.max_iter; ++k) {  // :295
         if (tid == 0) bicg_s1_body(&S, red, hist, a.cap);
         __syncthreads();
+        lap(9);
         if (S.h.status == DS_NEED_RESTART) residual(1);  // sets the status back to running
         if (S.h.status != DS_RUNNING) break;
         if (!iteration(false)) break;
@@ -459,7 +521,7 @@ struct BicgStab : spb_solver {
   DevBuf red;       // scal2 [2]
   DevBuf state;     // BicgState<T>
   DevBuf hist_d;
-  DevBuf fused_parts, fused_bar;  // single-kernel path
+  DevBuf fused_parts, fused_bar, fused_stats;  // single-kernel path
 
   // Single-kernel solve: one GPU, Jacobi or no preconditioner, matrix + vectors resident in L2.
   bool fused_eligible(const CsrMat<T>* Am, PcMode pcm) const {
@@ -529,23 +591,38 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   BicgState<T> init;
   memset(&init, 0, sizeof(init));
   init.h.status = DS_RUNNING;
-  init.tol = tol;
+  init.tol = (real_t<T>)tol;
   SPB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
 
   if (fused_eligible(Am, pcm)) {
     // the whole solve in one cooperative kernel (see bicg_fused_kernel)
     FusedArgs<T> fa{bufptr<int>(Am->indptr), bufptr<int>(Am->cols), bufptr<T>(Am->vals), (int)n, rhs, x, r, r0, p, y, v, t, z,
-                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol};
+                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol, nullptr};
+    const bool want_stats = getenv("SPB_FUSED_STATS") != nullptr;
+    if (want_stats) {
+      fused_stats.ensure(sizeof(long long) * 16);
+      SPB_CUDA(cudaMemsetAsync(fused_stats.p, 0, sizeof(long long) * 16, c->stream));
+      fa.stats = bufptr<long long>(fused_stats);
+    }
     c->gate = nullptr;
     if (pcm == PCM_JACOBI)
       launch_fused<T, true>(fa, n);
     else if (pcm == PCM_JACOBI_REAL)
-      launch_fused<double, true>(fa, n);
+      launch_fused<real_t<T>, true>(fa, n);
     else
       launch_fused<T, false>(fa, n);
     BicgState<T> fin;
     SPB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
+    if (want_stats) {
+      long long hs[16];
+      SPB_CUDA(cudaMemcpy(hs, fused_stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+      static const char* nm[10] = {"K1", "SpMV1", "K2", "SpMV2", "K3", "block partial", "reduction barrier", "partial sum", "plain barrier", "scalar step"};
+      const double its = (double)std::max<long long>(fin.h.its, 1);
+      fprintf(stderr, "[bicg_fused] clocks per iteration (CTA 0):");
+      for (int k = 0; k < 10; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)hs[k] / its);
+      fprintf(stderr, "\n");
+    }
     int rcf;
     if (fin.h.status == DS_OK || fin.h.status == DS_ZERO_RHS) {
       *iters = fin.h.res_iters;
@@ -588,8 +665,8 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
         if (first) bicg_k1<T, T, true, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)dinv);
         else bicg_k1<T, T, false, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)dinv);
       } else if (pcm == PCM_JACOBI_REAL) {
-        if (first) bicg_k1<T, double, true, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const double*)dinv);
-        else bicg_k1<T, double, false, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const double*)dinv);
+        if (first) bicg_k1<T, real_t<T>, true, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const real_t<T>*)dinv);
+        else bicg_k1<T, real_t<T>, false, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const real_t<T>*)dinv);
       } else {
         if (first) bicg_k1<T, T, true, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)nullptr);
         else bicg_k1<T, T, false, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v, p, r, y, (const T*)nullptr);
@@ -602,7 +679,7 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     {
       LaunchScope ls(c, FAM_VEC);
       if (pcm == PCM_JACOBI) bicg_k2<T, T, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const T*)dinv);
-      else if (pcm == PCM_JACOBI_REAL) bicg_k2<T, double, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const double*)dinv);
+      else if (pcm == PCM_JACOBI_REAL) bicg_k2<T, real_t<T>, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const real_t<T>*)dinv);
       else bicg_k2<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, r, v, z, (const T*)nullptr);
       check_launch("bicg_k2");
     }
@@ -750,8 +827,12 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
 }
 
 spb_solver* make_bicgstab(spb_op* A, int64_t size) {
-  if (A->dtype == SPB_F64) return new BicgStab<double>(A, size);
-  return new BicgStab<cplx>(A, size);
+  switch (A->dtype) {
+    case SPB_F64: return new BicgStab<double>(A, size);
+    case SPB_C128: return new BicgStab<cplx>(A, size);
+    case SPB_F32: return new BicgStab<float>(A, size);
+    default: return new BicgStab<cplxf>(A, size);
+  }
 }
 
 }  // namespace spb

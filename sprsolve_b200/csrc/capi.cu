@@ -37,6 +37,38 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 static void use_device(Ctx* c) { SPB_CUDA(cudaSetDevice(c->device)); }
 
+// Runs `stmt` with `T` bound to the scalar type of a dtype code (s / d / c / z, src/mkl_mat.rs:68-71).
+#define SPB_WITH_DTYPE(dt, ...)                        \
+  switch (dt) {                                        \
+    case SPB_F64: {                                    \
+      using T = double;                                \
+      __VA_ARGS__;                                     \
+    } break;                                           \
+    case SPB_C128: {                                   \
+      using T = cplx;                                  \
+      __VA_ARGS__;                                     \
+    } break;                                           \
+    case SPB_F32: {                                    \
+      using T = float;                                 \
+      __VA_ARGS__;                                     \
+    } break;                                           \
+    case SPB_C64: {                                    \
+      using T = cplxf;                                 \
+      __VA_ARGS__;                                     \
+    } break;                                           \
+    default:                                           \
+      SPB_FAIL(SPB_INVALID_ARG, "bad dtype");          \
+  }
+static size_t dtype_size(int dt) {
+  switch (dt) {
+    case SPB_F64: return sizeof(double);
+    case SPB_C128: return sizeof(cplx);
+    case SPB_F32: return sizeof(float);
+    case SPB_C64: return sizeof(cplxf);
+    default: SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  }
+}
+
 // All functions below were declared extern "C" in include/sprsolve_b200.h and keep C linkage.
 
 const char* spb_version(void) { return "sprsolve_b200 0.1.0 (sm_100a)"; }
@@ -243,12 +275,7 @@ int spb_csr_create(spb_ctx* c, int dtype, int64_t nrows, int64_t ncols, int64_t 
     return SPB_INCOMPATIBLE_FORMAT;
   }
   if (!c->dist) SPB_REQUIRE(row_begin == 0 && row_end == nrows, "row range needs a communicator");
-  if (dtype == SPB_F64)
-    *out = csr_from_host<double>(c, nrows, row_begin, row_end, indptr, indptr_bits, indices, values);
-  else if (dtype == SPB_C128)
-    *out = csr_from_host<cplx>(c, nrows, row_begin, row_end, indptr, indptr_bits, indices, values);
-  else
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  SPB_WITH_DTYPE(dtype, *out = csr_from_host<T>(c, nrows, row_begin, row_end, indptr, indptr_bits, indices, values));
   return SPB_OK;
   SPB_CATCH
 }
@@ -259,12 +286,7 @@ int spb_csr_create_stencil(spb_ctx* c, int kind, int dtype, int64_t nx, int64_t 
   SPB_REQUIRE(c && out, "null argument");
   *out = nullptr;
   use_device(c);
-  if (dtype == SPB_F64)
-    *out = csr_from_stencil<double>(c, kind, nx, ny, nz, params, nparams);
-  else if (dtype == SPB_C128)
-    *out = csr_from_stencil<cplx>(c, kind, nx, ny, nz, params, nparams);
-  else
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  SPB_WITH_DTYPE(dtype, *out = csr_from_stencil<T>(c, kind, nx, ny, nz, params, nparams));
   return SPB_OK;
   SPB_CATCH
 }
@@ -279,12 +301,7 @@ int spb_csc_create(spb_ctx* c, int dtype, int64_t nrows, int64_t ncols, const vo
     set_last_error("Not a square matrix");
     return SPB_INCOMPATIBLE_FORMAT;
   }
-  if (dtype == SPB_F64)
-    *out = csr_from_csc<double>(c, nrows, indptr, indptr_bits, row_indices, values);
-  else if (dtype == SPB_C128)
-    *out = csr_from_csc<cplx>(c, nrows, indptr, indptr_bits, row_indices, values);
-  else
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  SPB_WITH_DTYPE(dtype, *out = csr_from_csc<T>(c, nrows, indptr, indptr_bits, row_indices, values));
   return SPB_OK;
   SPB_CATCH
 }
@@ -299,12 +316,7 @@ int spb_csr_create_from_triplets(spb_ctx* c, int dtype, int64_t nrows, int64_t n
     set_last_error("Not a square matrix");
     return SPB_INCOMPATIBLE_FORMAT;
   }
-  if (dtype == SPB_F64)
-    *out = csr_from_triplets<double>(c, nrows, nnz, rows, cols, values);
-  else if (dtype == SPB_C128)
-    *out = csr_from_triplets<cplx>(c, nrows, nnz, rows, cols, values);
-  else
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  SPB_WITH_DTYPE(dtype, *out = csr_from_triplets<T>(c, nrows, nnz, rows, cols, values));
   return SPB_OK;
   SPB_CATCH
 }
@@ -314,12 +326,7 @@ int spb_csr_read_matrix_market(spb_ctx* c, int dtype, const char* path, spb_op**
   SPB_REQUIRE(c && out && path, "null argument");
   *out = nullptr;
   use_device(c);
-  if (dtype == SPB_F64)
-    *out = csr_from_matrix_market<double>(c, path);
-  else if (dtype == SPB_C128)
-    *out = csr_from_matrix_market<cplx>(c, path);
-  else
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
+  SPB_WITH_DTYPE(dtype, *out = csr_from_matrix_market<T>(c, path));
   return SPB_OK;
   SPB_CATCH
 }
@@ -328,10 +335,7 @@ static int rehint(spb_op* m) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR, "not a CSR matrix");
   use_device(m->ctx);
-  if (m->dtype == SPB_F64)
-    static_cast<CsrMat<double>*>(m)->autotune();
-  else
-    static_cast<CsrMat<cplx>*>(m)->autotune();
+  SPB_WITH_DTYPE(m->dtype, static_cast<CsrMat<T>*>(m)->autotune());
   return SPB_OK;
   SPB_CATCH
 }
@@ -351,7 +355,7 @@ int spb_op_size(spb_op* op, int64_t* n_global, int64_t* n_local, int64_t* row_be
 int spb_csr_nnz(spb_op* m, int64_t* nnz) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR && nnz, "not a CSR matrix");
-  *nnz = m->dtype == SPB_F64 ? static_cast<CsrMat<double>*>(m)->nnz : static_cast<CsrMat<cplx>*>(m)->nnz;
+  SPB_WITH_DTYPE(m->dtype, *nnz = static_cast<CsrMat<T>*>(m)->nnz);
   return SPB_OK;
   SPB_CATCH
 }
@@ -403,10 +407,7 @@ void csr_plan_info_impl(spb_op* op, int64_t* info) {
 int spb_csr_plan_info(spb_op* m, int64_t info[8]) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR && info, "not a CSR matrix");
-  if (m->dtype == SPB_F64)
-    csr_plan_info_impl<double>(m, info);
-  else
-    csr_plan_info_impl<cplx>(m, info);
+  SPB_WITH_DTYPE(m->dtype, csr_plan_info_impl<T>(m, info));
   return SPB_OK;
   SPB_CATCH
 }
@@ -415,10 +416,7 @@ int spb_csr_download(spb_op* m, int64_t* indptr64, int32_t* indices, void* value
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR, "not a CSR matrix");
   use_device(m->ctx);
-  if (m->dtype == SPB_F64)
-    csr_download(static_cast<CsrMat<double>*>(m), indptr64, indices, values);
-  else
-    csr_download(static_cast<CsrMat<cplx>*>(m), indptr64, indices, values);
+  SPB_WITH_DTYPE(m->dtype, csr_download(static_cast<CsrMat<T>*>(m), indptr64, indices, values));
   return SPB_OK;
   SPB_CATCH
 }
@@ -436,10 +434,7 @@ int spb_csr_diagonal(spb_op* m, void* diag_host) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR && diag_host, "not a CSR matrix");
   use_device(m->ctx);
-  if (m->dtype == SPB_F64)
-    csr_diag_to_host(static_cast<CsrMat<double>*>(m), diag_host);
-  else
-    csr_diag_to_host(static_cast<CsrMat<cplx>*>(m), diag_host);
+  SPB_WITH_DTYPE(m->dtype, csr_diag_to_host(static_cast<CsrMat<T>*>(m), diag_host));
   return SPB_OK;
   SPB_CATCH
 }
@@ -498,10 +493,7 @@ static int op_mul_checked(spb_op* op, const void* v_in, int64_t n_in, void* v_ou
     set_last_error("Dimension mismatch");
     return SPB_DIM_MISMATCH;
   }
-  if (op->dtype == SPB_F64)
-    op_mul_host<double>(op, v_in, v_out, with_dot, dot_out);
-  else
-    op_mul_host<cplx>(op, v_in, v_out, with_dot, dot_out);
+  SPB_WITH_DTYPE(op->dtype, op_mul_host<T>(op, v_in, v_out, with_dot, dot_out));
   return SPB_OK;
   SPB_CATCH
 }
@@ -517,10 +509,7 @@ int spb_op_mul_vec_dev(spb_op* op, const void* d_in, void* d_out) {
   SPB_TRY
   SPB_REQUIRE(op && d_in && d_out, "null argument");
   use_device(op->ctx);
-  if (op->dtype == SPB_F64)
-    op_mul_dev<double>(op, (const double*)d_in, (double*)d_out, false, nullptr);
-  else
-    op_mul_dev<cplx>(op, (const cplx*)d_in, (cplx*)d_out, false, nullptr);
+  SPB_WITH_DTYPE(op->dtype, op_mul_dev<T>(op, (const T*)d_in, (T*)d_out, false, nullptr));
   return SPB_OK;
   SPB_CATCH
 }
@@ -528,10 +517,7 @@ int spb_op_mul_vec_dot_dev(spb_op* op, const void* d_in, void* d_out, double out
   SPB_TRY
   SPB_REQUIRE(op && d_in && d_out && out, "null argument");
   use_device(op->ctx);
-  if (op->dtype == SPB_F64)
-    op_mul_dev<double>(op, (const double*)d_in, (double*)d_out, true, out);
-  else
-    op_mul_dev<cplx>(op, (const cplx*)d_in, (cplx*)d_out, true, out);
+  SPB_WITH_DTYPE(op->dtype, op_mul_dev<T>(op, (const T*)d_in, (T*)d_out, true, out));
   return SPB_OK;
   SPB_CATCH
 }
@@ -542,14 +528,12 @@ int spb_diag_precond_create(spb_ctx* c, int dtype, int diag_dtype, const void* d
   SPB_REQUIRE(c && out && (diag || n == 0) && n >= 0, "bad argument");
   *out = nullptr;
   use_device(c);
-  if (dtype == SPB_F64) {
-    SPB_REQUIRE(diag_dtype == SPB_F64, "real system needs a real diagonal");
-    *out = diag_from_host<double>(c, diag_dtype, diag, n);
-  } else if (dtype == SPB_C128) {
-    *out = diag_from_host<cplx>(c, diag_dtype, diag, n);
-  } else {
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype");
-  }
+  // V = T, or V = T::Real for a complex system (DiagPrecond<Complex64, f64> / <Complex32, f32>)
+  SPB_WITH_DTYPE(dtype, {
+    SPB_REQUIRE(diag_dtype == dtype || diag_dtype == ScalarTraits<real_t<T>>::dtype,
+                "the diagonal must have the system's scalar type or its real type");
+    *out = diag_from_host<T>(c, diag_dtype, diag, n);
+  });
   return SPB_OK;
   SPB_CATCH
 }
@@ -558,10 +542,7 @@ int spb_diag_precond_from_csr(spb_op* m, spb_op** out) {
   SPB_TRY
   SPB_REQUIRE(m && m->kind == OP_CSR && out, "not a CSR matrix");
   use_device(m->ctx);
-  if (m->dtype == SPB_F64)
-    *out = diag_from_csr(static_cast<CsrMat<double>*>(m));
-  else
-    *out = diag_from_csr(static_cast<CsrMat<cplx>*>(m));
+  SPB_WITH_DTYPE(m->dtype, *out = diag_from_csr(static_cast<CsrMat<T>*>(m)));
   return SPB_OK;
   SPB_CATCH
 }
@@ -575,17 +556,13 @@ int spb_gs_precond_create(spb_op* m, int mode, spb_op** out) {
     return SPB_INCOMPATIBLE_FORMAT;
   }
   use_device(m->ctx);
-  spb_op* op;
-  int64_t bad;
-  if (m->dtype == SPB_F64) {
-    auto* g = gs_create(static_cast<CsrMat<double>*>(m), mode);
+  spb_op* op = nullptr;
+  int64_t bad = -1;
+  SPB_WITH_DTYPE(m->dtype, {
+    auto* g = gs_create(static_cast<CsrMat<T>*>(m), mode);
     bad = g->bad_row;
     op = g;
-  } else {
-    auto* g = gs_create(static_cast<CsrMat<cplx>*>(m), mode);
-    bad = g->bad_row;
-    op = g;
-  }
+  });
   if (bad >= 0) {
     delete op;
     char b[128];
@@ -601,15 +578,11 @@ int spb_gs_precond_create(spb_op* m, int mode, spb_op** out) {
 int spb_gs_levels(spb_op* gs, int64_t* nf, int64_t* nb) {
   SPB_TRY
   SPB_REQUIRE(gs && gs->kind == OP_GS, "not a Gauss-Seidel operator");
-  if (gs->dtype == SPB_F64) {
-    auto* g = static_cast<GsOp<double>*>(gs);
+  SPB_WITH_DTYPE(gs->dtype, {
+    auto* g = static_cast<GsOp<T>*>(gs);
     if (nf) *nf = g->wfwd.ok ? g->wfwd.global_levels : g->fwd.nlevels;
     if (nb) *nb = g->wbwd.ok ? g->wbwd.global_levels : g->bwd.nlevels;
-  } else {
-    auto* g = static_cast<GsOp<cplx>*>(gs);
-    if (nf) *nf = g->wfwd.ok ? g->wfwd.global_levels : g->fwd.nlevels;
-    if (nb) *nb = g->wbwd.ok ? g->wbwd.global_levels : g->bwd.nlevels;
-  }
+  });
   return SPB_OK;
   SPB_CATCH
 }
@@ -637,10 +610,7 @@ void gs_schedule_info_impl(spb_op* gs, int64_t* info, int64_t* stats, int64_t ca
 int spb_gs_schedule_info(spb_op* gs, int64_t info[16], int64_t* stats, int64_t stats_cap) {
   SPB_TRY
   SPB_REQUIRE(gs && gs->kind == OP_GS, "not a Gauss-Seidel operator");
-  if (gs->dtype == SPB_F64)
-    gs_schedule_info_impl<double>(gs, info, stats, stats_cap);
-  else
-    gs_schedule_info_impl<cplx>(gs, info, stats, stats_cap);
+  SPB_WITH_DTYPE(gs->dtype, gs_schedule_info_impl<T>(gs, info, stats, stats_cap));
   return SPB_OK;
   SPB_CATCH
 }
@@ -686,6 +656,14 @@ template <>
 cplx scalar_of<cplx>(const double a[2]) {
   return cplx{a[0], a[1]};
 }
+template <>
+float scalar_of<float>(const double a[2]) {
+  return (float)a[0];
+}
+template <>
+cplxf scalar_of<cplxf>(const double a[2]) {
+  return cplxf{(float)a[0], (float)a[1]};
+}
 }  // namespace
 
 namespace {
@@ -698,7 +676,7 @@ void scale_host(Ctx* c, int64_t n, const double a[2], void* x) {
 template <typename T>
 void rscale_host(Ctx* c, int64_t n, double a, void* x) {
   HostVec<T> dx(c, x, n);
-  vec_rscale<T>(c, n, a, dx.p());
+  vec_rscale<T>(c, n, (real_t<T>)a, dx.p());
   dx.back(x);
 }
 template <typename T>
@@ -724,13 +702,7 @@ void axpby_host(Ctx* c, int64_t n, const double a[2], const void* x, const doubl
 }
 }  // namespace
 
-#define SPB_DISPATCH(dtype, fn, ...)               \
-  if ((dtype) == SPB_F64)                          \
-    fn<double>(__VA_ARGS__);                       \
-  else if ((dtype) == SPB_C128)                    \
-    fn<cplx>(__VA_ARGS__);                         \
-  else                                             \
-    SPB_FAIL(SPB_INVALID_ARG, "bad dtype")
+#define SPB_DISPATCH(dtype, fn, ...) SPB_WITH_DTYPE(dtype, fn<T>(__VA_ARGS__))
 
 int spb_vec_dot(spb_ctx* c, int dtype, int64_t n, const void* x, const void* y, double out[2]) {
   SPB_TRY
@@ -754,7 +726,8 @@ int spb_vec_norm2(spb_ctx* c, int dtype, int64_t n, const void* x, double* out) 
   use_device(c);
   double r[2];
   SPB_DISPATCH(dtype, vec_reduce_host, c, 2, n, x, nullptr, r);
-  *out = sqrt(r[0]);  // src/vecalg.rs:603-604
+  // src/vecalg.rs:603-604: the sum and the square root are T::Real
+  *out = (dtype == SPB_F32 || dtype == SPB_C64) ? (double)sqrtf((float)r[0]) : sqrt(r[0]);
   return SPB_OK;
   SPB_CATCH
 }
@@ -857,7 +830,7 @@ int spb_solver_solve(spb_solver* s, spb_op* precond, const void* rhs, int64_t n_
   SPB_REQUIRE((rhs && x) || n_rhs == 0, "null vector");
   if (precond && precond->dtype != s->dtype) SPB_FAIL(SPB_INVALID_ARG, "preconditioner dtype mismatch");
   Ctx* c = s->ctx;
-  const size_t esz = s->dtype == SPB_F64 ? sizeof(double) : sizeof(cplx);
+  const size_t esz = dtype_size(s->dtype);
   const size_t bytes = esz * (size_t)std::max<int64_t>(n_rhs, 1);
   s->stage_rhs.ensure(bytes);
   s->stage_x.ensure(bytes);

@@ -53,6 +53,14 @@ template <>
 __device__ __forceinline__ cplx make_val<cplx>(double re, double im) {
   return cplx{re, im};
 }
+template <>
+__device__ __forceinline__ float make_val<float>(double re, double) {
+  return (float)re;
+}
+template <>
+__device__ __forceinline__ cplxf make_val<cplxf>(double re, double im) {
+  return cplxf{(float)re, (float)im};
+}
 
 template <typename T>
 __global__ void stencil_fill_kernel(StencilDesc d, int64_t row_begin, int64_t n_local,
@@ -238,6 +246,8 @@ CsrMat<T>* csr_adopt_device(Ctx* ctx, int64_t n, int64_t nnz, DevBuf&& indptr32,
 }
 template CsrMat<double>* csr_adopt_device<double>(Ctx*, int64_t, int64_t, DevBuf&&, DevBuf&&, DevBuf&&);
 template CsrMat<cplx>* csr_adopt_device<cplx>(Ctx*, int64_t, int64_t, DevBuf&&, DevBuf&&, DevBuf&&);
+template CsrMat<float>* csr_adopt_device<float>(Ctx*, int64_t, int64_t, DevBuf&&, DevBuf&&, DevBuf&&);
+template CsrMat<cplxf>* csr_adopt_device<cplxf>(Ctx*, int64_t, int64_t, DevBuf&&, DevBuf&&, DevBuf&&);
 
 // ---------------------------------------------------------------- on-device generators
 void stencil_partition(int kind, int64_t nx, int64_t ny, int64_t nz, int world, int rank,
@@ -323,9 +333,12 @@ CsrMat<T>* csr_from_stencil(Ctx* ctx, int kind, int64_t nx, int64_t ny, int64_t 
   return m;
 }
 
-template CsrMat<double>* csr_from_host<double>(Ctx*, int64_t, int64_t, int64_t, const void*, int, const int32_t*, const void*);
-template CsrMat<cplx>* csr_from_host<cplx>(Ctx*, int64_t, int64_t, int64_t, const void*, int, const int32_t*, const void*);
-template CsrMat<double>* csr_from_stencil<double>(Ctx*, int, int64_t, int64_t, int64_t, const double*, int);
-template CsrMat<cplx>* csr_from_stencil<cplx>(Ctx*, int, int64_t, int64_t, int64_t, const double*, int);
+#define SPB_INST_CREATE(T)                                                                                                 \
+  template CsrMat<T>* csr_from_host<T>(Ctx*, int64_t, int64_t, int64_t, const void*, int, const int32_t*, const void*);   \
+  template CsrMat<T>* csr_from_stencil<T>(Ctx*, int, int64_t, int64_t, int64_t, const double*, int);
+SPB_INST_CREATE(double)
+SPB_INST_CREATE(cplx)
+SPB_INST_CREATE(float)
+SPB_INST_CREATE(cplxf)
 
 }  // namespace spb

@@ -467,13 +467,15 @@ void halo_exchange_begin(CsrMat<T>* m, const T* x) {
   }
   SPB_CUDA(cudaEventRecord(c->ev_pack, c->stream));
   SPB_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
-  const size_t per = sizeof(T) / sizeof(double);
+  // payload in units of the real type: f64 / f32 words
+  const size_t per = sizeof(T) / sizeof(real_t<T>);
+  const ncclDataType_t ndt = sizeof(real_t<T>) == 4 ? ncclFloat32 : ncclFloat64;
   SPB_NCCL(nccl().GroupStart());
   for (const HaloPeer& hp : m->peers) {
     if (hp.send_cnt)
-      SPB_NCCL(nccl().Send(bufptr<T>(m->sendbuf) + hp.send_off, hp.send_cnt * per, ncclFloat64, hp.rank, d->comm_halo, c->comm_stream));
+      SPB_NCCL(nccl().Send(bufptr<T>(m->sendbuf) + hp.send_off, hp.send_cnt * per, ndt, hp.rank, d->comm_halo, c->comm_stream));
     if (hp.recv_cnt)
-      SPB_NCCL(nccl().Recv(bufptr<T>(m->halo) + hp.recv_off, hp.recv_cnt * per, ncclFloat64, hp.rank, d->comm_halo, c->comm_stream));
+      SPB_NCCL(nccl().Recv(bufptr<T>(m->halo) + hp.recv_off, hp.recv_cnt * per, ndt, hp.rank, d->comm_halo, c->comm_stream));
   }
   SPB_NCCL(nccl().GroupEnd());
   SPB_CUDA(cudaEventRecord(c->ev_halo, c->comm_stream));
@@ -484,17 +486,16 @@ void halo_exchange_wait(CsrMat<T>* m) {
   SPB_CUDA(cudaStreamWaitEvent(m->ctx->stream, m->ctx->ev_halo, 0));
 }
 
-template void csr_localize<double>(CsrMat<double>*);
-template void csr_localize<cplx>(CsrMat<cplx>*);
-template void classify_tiles<double>(CsrMat<double>*);
-template void classify_tiles<cplx>(CsrMat<cplx>*);
-template void halo_exchange_begin<double>(CsrMat<double>*, const double*);
-template void halo_exchange_begin<cplx>(CsrMat<cplx>*, const cplx*);
-template void halo_exchange_wait<double>(CsrMat<double>*);
-template void halo_exchange_wait<cplx>(CsrMat<cplx>*);
-template void halo_put<double>(CsrMat<double>*, const double*);
-template void halo_put<cplx>(CsrMat<cplx>*, const cplx*);
-template void halo_release<double>(CsrMat<double>*);
-template void halo_release<cplx>(CsrMat<cplx>*);
+#define SPB_INST_DIST(T)                                              \
+  template void csr_localize<T>(CsrMat<T>*);                          \
+  template void classify_tiles<T>(CsrMat<T>*);                        \
+  template void halo_exchange_begin<T>(CsrMat<T>*, const T*);         \
+  template void halo_exchange_wait<T>(CsrMat<T>*);                    \
+  template void halo_put<T>(CsrMat<T>*, const T*);                    \
+  template void halo_release<T>(CsrMat<T>*);
+SPB_INST_DIST(double)
+SPB_INST_DIST(cplx)
+SPB_INST_DIST(float)
+SPB_INST_DIST(cplxf)
 
 }  // namespace spb

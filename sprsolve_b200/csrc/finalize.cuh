@@ -30,14 +30,14 @@ __global__ void finalize_reduce_k(const Acc<T>* partials, int64_t nblocks, scal2
   }
   if (MODE == 1) {
     peer_allreduce_dd(loc, pp);
-    if (t < 4) fin[t] = loc[t];
+    if (t < 4) fin[t] = round_to_real<T>(loc[t]);
   } else {
     __syncthreads();
     if (MODE == 2) {
       if (t < 8) dd_out[t] = loc[t];
       return;
     }
-    if (t < 4) fin[t] = loc[2 * t] + loc[2 * t + 1];
+    if (t < 4) fin[t] = round_to_real<T>(loc[2 * t] + loc[2 * t + 1]);
   }
   __syncthreads();
   if (t < 2) red[t] = scal2{fin[2 * t], fin[2 * t + 1]};
@@ -46,7 +46,7 @@ __global__ void finalize_reduce_k(const Acc<T>* partials, int64_t nblocks, scal2
 }
 
 // NCCL transport: gathered = [world][8]; rank-order double-double sum of every pair, one rounding.
-template <typename Tail>
+template <typename T, typename Tail>
 __global__ void finish_gathered_k(const double* gathered, int world, scal2* red, Tail tail) {
   __shared__ double fin[4];
   const int t = threadIdx.x;
@@ -56,7 +56,7 @@ __global__ void finish_gathered_k(const double* gathered, int world, scal2* red,
       lo += gathered[8 * q + 2 * t + 1];
       dd_add(hi, lo, gathered[8 * q + 2 * t]);
     }
-    fin[t] = hi + lo;
+    fin[t] = round_to_real<T>(hi + lo);
   }
   __syncthreads();
   if (t < 2) red[t] = scal2{fin[2 * t], fin[2 * t + 1]};
@@ -79,7 +79,7 @@ void finalize_reduce_tail(Ctx* c, const Acc<T>* partials, int64_t nblocks, scal2
     double* recv = send + 8;
     finalize_reduce_k<T, 2, NoTail><<<1, 256, 0, c->stream>>>(partials, nblocks, red, PeerPtrs{}, send, NoTail{});
     SPB_NCCL(nccl().AllGather(send, recv, 8, ncclFloat64, d->comm, c->stream));
-    finish_gathered_k<Tail><<<1, 32, 0, c->stream>>>(recv, d->world, red, tail);
+    finish_gathered_k<T, Tail><<<1, 32, 0, c->stream>>>(recv, d->world, red, tail);
   }
   check_launch("finalize_reduce");
 }

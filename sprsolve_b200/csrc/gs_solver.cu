@@ -7,31 +7,34 @@
 
 namespace spb {
 
+template <typename R>
 struct GsState {
   StateHead h;
-  double tol2, eps;
+  R tol2, eps;  // T::Real
 };
 
-__global__ void gs_s_bnorm(GsState* st, const scal2* red) {
-  st->tol2 = st->eps * sqrt(red[0].re);  // src/gauss_seidel.rs:83,87
+template <typename R>
+__global__ void gs_s_bnorm(GsState<R>* st, const scal2* red) {
+  st->tol2 = st->eps * sqrt_r((R)red[0].re);  // src/gauss_seidel.rs:83,87
 }
 
-__global__ void gs_s_check(GsState* st, const scal2* red, long long it, double* hist, long long cap) {
+template <typename R>
+__global__ void gs_s_check(GsState<R>* st, const scal2* red, long long it, double* hist, long long cap) {
   if (st->h.status != DS_RUNNING) return;
-  const double res = sqrt(red[0].re);  // :104 / :133
-  if (hist && it < cap) hist[it] = res;
+  const R res = sqrt_r((R)red[0].re);  // :104 / :133
+  if (hist && it < cap) hist[it] = (double)res;
   if (it + 1 > st->h.hist_len) st->h.hist_len = it + 1;
   st->h.its = it;
   if (res <= st->tol2) {  // :106-108 / :135-137
     st->h.status = DS_OK;
     st->h.res_iters = it == 0 ? 1 : it;
-    st->h.res_resid = res;
+    st->h.res_resid = (double)res;
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kVecThreads)
-gs_k_resid(const GsState* st, int64_t n, const T* rhs, T* res, Acc<T>* partials) {
+gs_k_resid(const GsState<real_t<T>>* st, int64_t n, const T* rhs, T* res, Acc<T>* partials) {
   Acc<T> e0 = zero_of<Acc<T>>();
   if (st->h.status == DS_RUNNING) {
     const T m1 = neg(one_of<T>());
@@ -60,7 +63,7 @@ struct GaussSeidelSolver : spb_solver {
     xalt.alloc(sizeof(T) * n1);
     partials.alloc(sizeof(Acc<T>) * 2 * (size_t)(vec_max_grid(ctx) + 1));
     red.alloc(sizeof(scal2) * 2);
-    state.alloc(sizeof(GsState));
+    state.alloc(sizeof(GsState<real_t<T>>));
   }
   ~GaussSeidelSolver() override { delete gs; }
   int solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_iter, double eps, int64_t* iters,
@@ -86,7 +89,8 @@ int GaussSeidelSolver<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int
   auto* Am = static_cast<CsrMat<T>*>(A);
   const T* rhs = (const T*)d_rhs;
   T* xbuf[2] = {(T*)d_x, bufptr<T>(xalt)};
-  auto* st = bufptr<GsState>(state);
+  using R = real_t<T>;
+  auto* st = bufptr<GsState<R>>(state);
   scal2* redp = bufptr<scal2>(red);
   Acc<T>* parts = bufptr<Acc<T>>(partials);
   T* resv = bufptr<T>(res);
@@ -97,10 +101,10 @@ int GaussSeidelSolver<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int
     hist_d.ensure(sizeof(double) * cap);
     hd = bufptr<double>(hist_d);
   }
-  GsState init;
+  GsState<R> init;
   memset(&init, 0, sizeof(init));
   init.h.status = DS_RUNNING;
-  init.eps = eps;
+  init.eps = (R)eps;
   SPB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
   int rc = SPB_OK;
   Poller poller(c);
@@ -109,7 +113,7 @@ int GaussSeidelSolver<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int
     vec_reduce<T>(c, 2, n, rhs, rhs, parts, redp);  // ||b||^2, :83
     {
       LaunchScope ls(c, FAM_SCALAR);
-      gs_s_bnorm<<<1, 1, 0, c->stream>>>(st, redp);
+      gs_s_bnorm<R><<<1, 1, 0, c->stream>>>(st, redp);
       check_launch("gs_s_bnorm");
     }
     c->gate = &st->h.status;
@@ -132,7 +136,7 @@ int GaussSeidelSolver<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int
           finalize_partials<T>(c, parts, grid, redp);
           {
             LaunchScope ls(c, FAM_SCALAR);
-            gs_s_check<<<1, 1, 0, c->stream>>>(st, redp, (long long)it, hd, cap);
+            gs_s_check<R><<<1, 1, 0, c->stream>>>(st, redp, (long long)it, hd, cap);
             check_launch("gs_s_check");
           }
         }
@@ -175,8 +179,12 @@ spb_solver* make_gauss_seidel(spb_op* A) {
     set_last_error("Not in CSR format");  // src/gauss_seidel.rs:22-26
     throw SpbError{SPB_INCOMPATIBLE_FORMAT};
   }
-  if (A->dtype == SPB_F64) return new GaussSeidelSolver<double>(A);
-  return new GaussSeidelSolver<cplx>(A);
+  switch (A->dtype) {
+    case SPB_F64: return new GaussSeidelSolver<double>(A);
+    case SPB_C128: return new GaussSeidelSolver<cplx>(A);
+    case SPB_F32: return new GaussSeidelSolver<float>(A);
+    default: return new GaussSeidelSolver<cplxf>(A);
+  }
 }
 
 }  // namespace spb

@@ -63,6 +63,12 @@ static const int WAVE_MAX_STAGES = 8;
 static const int WAVE_FIXED = 256;     // barriers, ticket slot, zero slot
 static const int WAVE_ZERO_OFF = 192;  // 16 bytes of +0.0: target of the ELL padding entries
 #define SPB_GS_SENTINEL 0xFFFFDEADBEEF5EEDULL
+#define SPB_GS_SENTINEL32 0xFFDEAD5Eu /* f32 / Complex32 slots: a NaN payload in every 32-bit word */
+// the 64-bit word the pre-pass fills the mailbox with: one f64 sentinel or two f32 sentinels
+template <typename T>
+__host__ __device__ inline unsigned long long wave_sentinel_fill() {
+  return sizeof(real_t<T>) == 4 ? (((unsigned long long)SPB_GS_SENTINEL32 << 32) | SPB_GS_SENTINEL32) : SPB_GS_SENTINEL;
+}
 
 __host__ __device__ inline int wave_a16(long long v) { return (int)((v + 15) & ~15LL); }
 
@@ -105,15 +111,33 @@ __device__ __forceinline__ cplx wv_poll(const cplx* p) {
   asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.re), "=d"(v.im) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ float wv_poll(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ cplxf wv_poll(const cplxf* p) {
+  cplxf v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.re), "=f"(v.im) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ bool wv_is_sentinel(double v) {
   return (unsigned long long)__double_as_longlong(v) == SPB_GS_SENTINEL;
 }
 __device__ __forceinline__ bool wv_is_sentinel(cplx v) { return wv_is_sentinel(v.re) || wv_is_sentinel(v.im); }
+__device__ __forceinline__ bool wv_is_sentinel(float v) { return (unsigned)__float_as_int(v) == SPB_GS_SENTINEL32; }
+__device__ __forceinline__ bool wv_is_sentinel(cplxf v) { return wv_is_sentinel(v.re) || wv_is_sentinel(v.im); }
 __device__ __forceinline__ void wv_publish(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 __device__ __forceinline__ void wv_publish(cplx* p, cplx v) {
   asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.re), "d"(v.im) : "memory");
+}
+__device__ __forceinline__ void wv_publish(float* p, float v) {
+  asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void wv_publish(cplxf* p, cplxf v) {
+  asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.re), "f"(v.im) : "memory");
 }
 template <typename T>
 __device__ __forceinline__ T wv_lds(uint32_t addr);
@@ -127,6 +151,18 @@ template <>
 __device__ __forceinline__ cplx wv_lds<cplx>(uint32_t addr) {
   cplx v;
   asm volatile("ld.volatile.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(addr) : "memory");
+  return v;
+}
+template <>
+__device__ __forceinline__ float wv_lds<float>(uint32_t addr) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+template <>
+__device__ __forceinline__ cplxf wv_lds<cplxf>(uint32_t addr) {
+  cplxf v;
+  asm volatile("ld.volatile.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.re), "=f"(v.im) : "r"(addr) : "memory");
   return v;
 }
 // x value at a resolved shared-memory address; spins while the slot still holds the sentinel
@@ -175,7 +211,7 @@ __global__ void __launch_bounds__(kVecThreads) gs_wave_prep_kernel(int64_t mb8, 
                                                                     int* ticket, const int* gate, int gate_value) {
   if (gate && *gate != gate_value) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) ticket[0] = 0;
-  SPB_GRID_STRIDE(i, mb8) mailbox8[i] = SPB_GS_SENTINEL;
+  SPB_GRID_STRIDE(i, mb8) mailbox8[i] = wave_sentinel_fill<T>();
   SPB_GRID_STRIDE(p, rhs_slots) {
     const int r = rowmap[p];
     rhsp[p] = r >= 0 ? rhs[r] : zero_of<T>();
@@ -442,7 +478,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   const int64_t align_el = std::max<int64_t>(1, 16 / (int64_t)sizeof(T));  // elements per 16 bytes
   auto align_slots = [&](int64_t v) { return (v + align_el - 1) / align_el * align_el; };
   auto pad4 = [](int v) { return (v + 3) & ~3; };
-  const unsigned long long sentinel = SPB_GS_SENTINEL;
+  const unsigned long long sentinel = wave_sentinel_fill<T>();
 
   std::vector<int> lev(n, 0);
   std::vector<unsigned char> stat;
@@ -780,7 +816,7 @@ template <typename T, typename IP>
 static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other) {
   Ctx* c = M->ctx;
   CsrMat<T>* A = M->A;
-  const int64_t mb8 = ws.mailbox_slots * (int64_t)(sizeof(T) / 8);
+  const int64_t mb8 = (ws.mailbox_slots * (int64_t)sizeof(T) + 7) / 8;  // (the allocation carries 4 spare slots)
   const int64_t work = std::max(mb8, ws.rhs_slots);
   LaunchScope lsc(c, FAM_PRECOND);
   auto kern = ws.backward ? gs_wave_prep_kernel<T, IP, true> : gs_wave_prep_kernel<T, IP, false>;
@@ -836,5 +872,7 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   template void wave_sweep<T>(GsOp<T>*, WaveSched&, const T*, const T*, T*);
 SPB_INST_WAVE(double)
 SPB_INST_WAVE(cplx)
+SPB_INST_WAVE(float)
+SPB_INST_WAVE(cplxf)
 
 }  // namespace spb

@@ -283,5 +283,7 @@ CsrMat<T>* csr_from_matrix_market(Ctx* c, const char* path) {
   template CsrMat<T>* csr_from_matrix_market<T>(Ctx*, const char*);
 SPB_INST_INGEST(double)
 SPB_INST_INGEST(cplx)
+SPB_INST_INGEST(float)
+SPB_INST_INGEST(cplxf)
 
 }  // namespace spb

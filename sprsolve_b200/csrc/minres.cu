@@ -20,7 +20,7 @@ template <typename T>
 struct MinresState {
   StateHead h;
   T c, c_old, eta, alpha, nalpha, nbeta, nr2, nr3, tau;
-  double s, s_old, beta, beta_new, beta_one, res_norm, threshold, rhs_norm, tol, inv_beta, r1_inv;
+  real_t<T> s, s_old, beta, beta_new, beta_one, res_norm, threshold, rhs_norm, tol, inv_beta, r1_inv;  // T::Real
 };
 
 __device__ __forceinline__ void mr_hist_put(StateHead& h, double* hist, long long cap, long long k, double v) {
@@ -30,29 +30,33 @@ __device__ __forceinline__ void mr_hist_put(StateHead& h, double* hist, long lon
 
 template <typename T>
 __global__ void mr_s_rhs(MinresState<T>* st, const scal2* red) {
-  const double rhs_norm = sqrt(red[0].re);  // minres.rs:51
+  using R = real_t<T>;
+  const R rhs_norm = sqrt_r((R)red[0].re);  // minres.rs:51
   st->rhs_norm = rhs_norm;
   st->threshold = st->tol * rhs_norm;       // :57
-  if (rhs_norm <= SPB_EPS) {                // :52-56
+  if (rhs_norm <= eps_of<T>()) {            // :52-56
     st->h.status = DS_ZERO_RHS;
     st->h.res_iters = 0;
-    st->h.res_resid = rhs_norm;
+    st->h.res_resid = (double)rhs_norm;
   }
 }
 
 // precond: b2 = <v_new, w_new>; validity test minres.rs:236-244 / :279-287
 template <typename T>
-__device__ __forceinline__ bool beta_from_precond(const scal2& b2, double* beta_new) {
-  if (b2.re < SPB_EPS || b2.im > SPB_EPS * b2.re) return false;
-  *beta_new = sqrt(b2.re);
+__device__ __forceinline__ bool beta_from_precond(const scal2& b2, real_t<T>* beta_new) {
+  using R = real_t<T>;
+  const R re = (R)b2.re, im = (R)b2.im;
+  if (re < eps_of<T>() || im > eps_of<T>() * re) return false;
+  *beta_new = sqrt_r(re);
   return true;
 }
 
 template <typename T>
 __global__ void mr_s_init(MinresState<T>* st, const scal2* red, const scal2* b2, int precond) {
   if (st->h.status != DS_RUNNING) return;
-  st->res_norm = sqrt(red[0].re);  // :81 / :231
-  double beta_new;
+  using R = real_t<T>;
+  st->res_norm = sqrt_r((R)red[0].re);  // :81 / :231
+  R beta_new;
   if (precond) {
     if (!beta_from_precond<T>(*b2, &beta_new)) {
       st->h.status = DS_INVALID_PRECOND;
@@ -64,11 +68,11 @@ __global__ void mr_s_init(MinresState<T>* st, const scal2* red, const scal2* b2,
   }
   st->beta_new = beta_new;
   st->beta_one = beta_new;           // :83 / :246
-  st->inv_beta = 1.0 / beta_new;     // :84 / :248
+  st->inv_beta = (R)1 / beta_new;    // :84 / :248
   st->c = one_of<T>();               // :60-64
   st->c_old = one_of<T>();
-  st->s = 0.0;
-  st->s_old = 0.0;
+  st->s = (R)0;
+  st->s_old = (R)0;
   st->eta = one_of<T>();
 }
 
@@ -92,7 +96,8 @@ template <typename T, bool CS>
 __device__ __forceinline__ void mr_s_givens_body(MinresState<T>* st, const scal2* red, const scal2* b2, int precond,
                                                  long long its, double* hist, long long cap) {
   if (st->h.status != DS_RUNNING) return;
-  double beta_new;
+  using R = real_t<T>;
+  R beta_new;
   if (precond) {
     if (!beta_from_precond<T>(*b2, &beta_new)) {  // :279-287
       st->h.status = DS_INVALID_PRECOND;
@@ -100,34 +105,34 @@ __device__ __forceinline__ void mr_s_givens_body(MinresState<T>* st, const scal2
       return;
     }
   } else {
-    beta_new = sqrt(red[0].re);  // :120
+    beta_new = sqrt_r((R)red[0].re);  // :120
   }
   st->beta_new = beta_new;
-  st->inv_beta = 1.0 / beta_new;  // :121 / :289
-  const double beta = st->beta, s = st->s, s_old = st->s_old;
+  st->inv_beta = (R)1 / beta_new;  // :121 / :289
+  const R beta = st->beta, s = st->s, s_old = st->s_old;
   const T c = st->c, c_old = st->c_old, alpha = st->alpha;
   // Givens rotation, minres.rs:132-148 ; cs_minres.rs:119-134 (conjugations differ)
-  const double r3 = s_old * beta;
+  const R r3 = s_old * beta;
   const T tr = CS ? mul_real(conj_of(c_old), beta) : mul_real(c_old, beta);
   const T r2 = add(mul_real(alpha, s), mul(c, tr));
   const T r1_hat = CS ? sub(mul(conj_of(c), alpha), mul_real(tr, s)) : sub(mul(c, alpha), mul_real(tr, s));
-  const double r1_inv = 1.0 / sqrt(square(r1_hat) + beta_new * beta_new);
+  const R r1_inv = (R)1 / sqrt_r(square(r1_hat) + beta_new * beta_new);
   st->c_old = c;
   st->s_old = s;
   const T c_new = CS ? mul_real(conj_of(r1_hat), r1_inv) : mul_real(r1_hat, r1_inv);
-  const double s_new = beta_new * r1_inv;
+  const R s_new = beta_new * r1_inv;
   st->c = c_new;
   st->s = s_new;
   st->nr2 = neg(r2);                 // axpy(-r2, p_old, p), :158
   st->nr3 = from_real<T>(-r3);       // axpy(T::from_real(-r3), p_oold, p), :159
   st->r1_inv = r1_inv;               // rscale(r1_inv, p), :160
   st->tau = mul_real(mul(c_new, st->eta), st->beta_one);  // :162
-  st->res_norm *= fabs(s_new);       // :164
-  mr_hist_put(st->h, hist, cap, its, st->res_norm / st->rhs_norm);
+  st->res_norm *= fabs_r(s_new);     // :164
+  mr_hist_put(st->h, hist, cap, its, (double)(st->res_norm / st->rhs_norm));
   if (st->res_norm < st->threshold) {  // :165-167 (the x update of this iteration still runs)
     st->h.status = DS_OK;
     st->h.res_iters = its;
-    st->h.res_resid = st->res_norm / st->rhs_norm;
+    st->h.res_resid = (double)(st->res_norm / st->rhs_norm);
     return;
   }
   st->eta = mul_real(st->eta, -s_new);  // :168
@@ -179,7 +184,7 @@ template <typename T>
 __global__ void __launch_bounds__(kVecThreads)
 mr_k_scale(const MinresState<T>* st, int64_t n, T* v_new, T* w_new) {
   if (st->h.status != DS_RUNNING) return;
-  const double ts = st->inv_beta;
+  const real_t<T> ts = st->inv_beta;
   SPB_GRID_STRIDE(i, n) {
     v_new[i] = mul_real(v_new[i], ts);              // rscale, :84 / :249
     if (w_new) w_new[i] = mul_real(w_new[i], ts);   // :250
@@ -215,7 +220,7 @@ mr_k2(const MinresState<T>* st, long long its, int64_t n, const T* q, const T* p
   const int status = st->h.status;
   if (!(status == DS_RUNNING || (status == DS_OK && st->h.res_iters == its))) return;
   const T nr2 = st->nr2, nr3 = st->nr3, tau = st->tau;
-  const double r1_inv = st->r1_inv, ts = st->inv_beta;
+  const real_t<T> r1_inv = st->r1_inv, ts = st->inv_beta;
   SPB_GRID_STRIDE(i, n) {
     v_new[i] = mul_real(v_new[i], ts);             // rscale(1/beta_new, v_new), :121 / :290
     if (w_new) w_new[i] = mul_real(w_new[i], ts);  // :291
@@ -287,7 +292,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
   MinresState<T> init;
   memset(&init, 0, sizeof(init));
   init.h.status = DS_RUNNING;
-  init.tol = tol;
+  init.tol = (real_t<T>)tol;
   SPB_CUDA(cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
 
   auto scalar = [&](auto kernel, auto... args) {
@@ -329,7 +334,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
       if (pcm == PCM_JACOBI)
         mr_k_init<T, T, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const T*)dinv, parts);
       else if (pcm == PCM_JACOBI_REAL)
-        mr_k_init<T, double, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const double*)dinv, parts);
+        mr_k_init<T, real_t<T>, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const real_t<T>*)dinv, parts);
       else
         mr_k_init<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const T*)nullptr, parts);
       check_launch("mr_k_init");
@@ -369,7 +374,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
             if (pcm == PCM_JACOBI)
               mr_k1<T, T, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)dinv, parts);
             else if (pcm == PCM_JACOBI_REAL)
-              mr_k1<T, double, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const double*)dinv, parts);
+              mr_k1<T, real_t<T>, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const real_t<T>*)dinv, parts);
             else
               mr_k1<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)nullptr, parts);
             check_launch("mr_k1");
@@ -435,8 +440,12 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
 }
 
 spb_solver* make_minres(spb_op* A, int64_t size, bool cs) {
-  if (A->dtype == SPB_F64) return new MinRes<double>(A, size, cs);
-  return new MinRes<cplx>(A, size, cs);
+  switch (A->dtype) {
+    case SPB_F64: return new MinRes<double>(A, size, cs);
+    case SPB_C128: return new MinRes<cplx>(A, size, cs);
+    case SPB_F32: return new MinRes<float>(A, size, cs);
+    default: return new MinRes<cplxf>(A, size, cs);
+  }
 }
 
 }  // namespace spb

@@ -26,6 +26,14 @@ template <>
 __global__ void reciprocal_kernel<cplx>(int64_t n, cplx* d) {
   SPB_GRID_STRIDE(i, n) d[i] = divi(cplx{1.0, 0.0}, d[i]);
 }
+template <>
+__global__ void reciprocal_kernel<float>(int64_t n, float* d) {
+  SPB_GRID_STRIDE(i, n) d[i] = 1.0f / d[i];
+}
+template <>
+__global__ void reciprocal_kernel<cplxf>(int64_t n, cplxf* d) {
+  SPB_GRID_STRIDE(i, n) d[i] = divi(cplxf{1.0f, 0.0f}, d[i]);
+}
 
 template <typename T, typename V>
 __global__ void __launch_bounds__(kVecThreads) diag_apply_kernel(int64_t n, const V* dinv, const T* in, T* out, const int* gate, int gate_value) {
@@ -41,16 +49,16 @@ DiagOp<T>* diag_from_host(Ctx* ctx, int diag_dtype, const void* diag, int64_t n)
     op->kind = OP_DIAG;
     op->dtype = ScalarTraits<T>::dtype;
     op->n_global = op->n_local = n;
-    op->real_diag = ScalarTraits<T>::is_complex && diag_dtype == SPB_F64;
-    const size_t esz = op->real_diag ? sizeof(double) : sizeof(T);
+    op->real_diag = ScalarTraits<T>::is_complex && diag_dtype == ScalarTraits<real_t<T>>::dtype;
+    const size_t esz = op->real_diag ? sizeof(real_t<T>) : sizeof(T);
     op->dinv.alloc(esz * (size_t)std::max<int64_t>(n, 1));
     if (n) SPB_CUDA(cudaMemcpyAsync(op->dinv.p, diag, esz * n, cudaMemcpyHostToDevice, ctx->stream));
     if (n) {
       LaunchScope ls(ctx, FAM_PRECOND);
       if (op->real_diag || !ScalarTraits<T>::is_complex)
-        reciprocal_kernel<double><<<vec_grid(ctx, n), kVecThreads, 0, ctx->stream>>>(n, bufptr<double>(op->dinv));
+        reciprocal_kernel<real_t<T>><<<vec_grid(ctx, n), kVecThreads, 0, ctx->stream>>>(n, bufptr<real_t<T>>(op->dinv));
       else
-        reciprocal_kernel<cplx><<<vec_grid(ctx, n), kVecThreads, 0, ctx->stream>>>(n, bufptr<cplx>(op->dinv));
+        reciprocal_kernel<T><<<vec_grid(ctx, n), kVecThreads, 0, ctx->stream>>>(n, bufptr<T>(op->dinv));
       check_launch("reciprocal_kernel");
     }
     SPB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -74,7 +82,7 @@ __global__ void csr_diag_kernel(const IP* indptr, const int* cols, const T* vals
       }
     diag[r] = d;
     // src/gauss_seidel.rs:72-78: missing diagonal or |d|^2 < eps
-    if (bad_row && (!found || square(d) < SPB_EPS)) atomicMin(bad_row, (unsigned long long)r);
+    if (bad_row && (!found || square(d) < eps_of<T>())) atomicMin(bad_row, (unsigned long long)r);
   }
 }
 
@@ -130,7 +138,7 @@ void diag_apply(DiagOp<T>* M, const T* in, T* out) {
   if (n == 0) return;
   LaunchScope ls(c, FAM_PRECOND);
   if (M->real_diag)
-    diag_apply_kernel<T, double><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, bufptr<double>(M->dinv), in, out, c->gate, c->gate_value);
+    diag_apply_kernel<T, real_t<T>><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, bufptr<real_t<T>>(M->dinv), in, out, c->gate, c->gate_value);
   else
     diag_apply_kernel<T, T><<<vec_grid(c, n), kVecThreads, 0, c->stream>>>(n, bufptr<T>(M->dinv), in, out, c->gate, c->gate_value);
   check_launch("diag_apply_kernel");
@@ -141,6 +149,11 @@ __device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
 __device__ __forceinline__ cplx ld_cg(const cplx* p) {
   const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
   return cplx{v.x, v.y};
+}
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ cplxf ld_cg(const cplxf* p) {
+  const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  return cplxf{v.x, v.y};
 }
 
 // All CTAs are co-resident (cooperative launch), so a counter barrier cannot deadlock.
@@ -429,5 +442,7 @@ void op_apply(spb_op* op, const T* in, T* out) {
   template void op_apply<T>(spb_op*, const T*, T*);
 SPB_INST(double)
 SPB_INST(cplx)
+SPB_INST(float)
+SPB_INST(cplxf)
 
 }  // namespace spb

@@ -7,7 +7,7 @@ namespace spb {
 
 template <typename T>
 struct DiagOp : spb_op {
-  DevBuf dinv;        // T or double (real_diag) [n]: 1/diag, src/precond.rs:20-24
+  DevBuf dinv;        // T or T::Real (real_diag) [n]: 1/diag, src/precond.rs:20-24
   bool real_diag = false;
 };
 

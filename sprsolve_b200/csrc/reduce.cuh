@@ -25,25 +25,42 @@ __device__ __forceinline__ double shfl_down(double v, int d) {
 __device__ __forceinline__ cplx shfl_down(cplx v, int d) {
   return cplx{__shfl_down_sync(0xffffffffu, v.re, d), __shfl_down_sync(0xffffffffu, v.im, d)};
 }
+__device__ __forceinline__ float shfl_down(float v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ cplxf shfl_down(cplxf v, int d) {
+  return cplxf{__shfl_down_sync(0xffffffffu, v.re, d), __shfl_down_sync(0xffffffffu, v.im, d)};
+}
 
 // ---- double-double accumulators -----------------------------------------------------------------
-template <typename T>
-struct Acc;
-template <>
-struct __align__(16) Acc<double> {
+// One real and one complex accumulator type, shared by the f64 and the f32 scalars: a product of two
+// floats is exact in double, so the f32 types feed the same (hi, lo) pairs and are rounded to float
+// at the very end (scalar.cuh: round_to_real).
+struct __align__(16) AccR {
   double hi, lo;
 };
-template <>
-struct __align__(16) Acc<cplx> {
+struct __align__(16) AccC {
   double rh, rl, ih, il;
 };
+template <typename T>
+struct AccOf {
+  using type = AccR;
+};
 template <>
-SPB_HD Acc<double> zero_of<Acc<double>>() {
-  return Acc<double>{0.0, 0.0};
+struct AccOf<cplx> {
+  using type = AccC;
+};
+template <>
+struct AccOf<cplxf> {
+  using type = AccC;
+};
+template <typename T>
+using Acc = typename AccOf<T>::type;
+template <>
+SPB_HD AccR zero_of<AccR>() {
+  return AccR{0.0, 0.0};
 }
 template <>
-SPB_HD Acc<cplx> zero_of<Acc<cplx>>() {
-  return Acc<cplx>{0.0, 0.0, 0.0, 0.0};
+SPB_HD AccC zero_of<AccC>() {
+  return AccC{0.0, 0.0, 0.0, 0.0};
 }
 // (hi, lo) += x, x an exact double: error-free two-sum on hi, the error goes to lo
 __device__ __forceinline__ void dd_add(double& hi, double& lo, double x) {
@@ -58,45 +75,58 @@ __device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double a, do
   lo += __fma_rn(a, b, -p);
   dd_add(hi, lo, p);
 }
-__device__ __forceinline__ void acc_prod(Acc<double>& a, double x, double y) { dd_add_prod(a.hi, a.lo, x, y); }
-__device__ __forceinline__ void acc_prod(Acc<cplx>& a, cplx x, cplx y) {  // a += x * y
+__device__ __forceinline__ void acc_prod(AccR& a, double x, double y) { dd_add_prod(a.hi, a.lo, x, y); }
+__device__ __forceinline__ void acc_prod(AccC& a, cplx x, cplx y) {  // a += x * y
   dd_add_prod(a.rh, a.rl, x.re, y.re);
   dd_add_prod(a.rh, a.rl, -x.im, y.im);
   dd_add_prod(a.ih, a.il, x.re, y.im);
   dd_add_prod(a.ih, a.il, x.im, y.re);
 }
-__device__ __forceinline__ void acc_sq(Acc<double>& a, double x) { dd_add_prod(a.hi, a.lo, x, x); }  // a += |x|^2
-__device__ __forceinline__ void acc_sq(Acc<cplx>& a, cplx x) {
+__device__ __forceinline__ void acc_sq(AccR& a, double x) { dd_add_prod(a.hi, a.lo, x, x); }  // a += |x|^2
+__device__ __forceinline__ void acc_sq(AccC& a, cplx x) {
   dd_add_prod(a.rh, a.rl, x.re, x.re);
   dd_add_prod(a.rh, a.rl, x.im, x.im);
 }
-__device__ __forceinline__ Acc<double> add(Acc<double> a, Acc<double> b) {
+// f32 operands: the product is exact in double (24 + 24 significand bits), no error term
+__device__ __forceinline__ void acc_prod(AccR& a, float x, float y) { dd_add(a.hi, a.lo, (double)x * (double)y); }
+__device__ __forceinline__ void acc_prod(AccC& a, cplxf x, cplxf y) {
+  dd_add(a.rh, a.rl, (double)x.re * (double)y.re);
+  dd_add(a.rh, a.rl, -(double)x.im * (double)y.im);
+  dd_add(a.ih, a.il, (double)x.re * (double)y.im);
+  dd_add(a.ih, a.il, (double)x.im * (double)y.re);
+}
+__device__ __forceinline__ void acc_sq(AccR& a, float x) { dd_add(a.hi, a.lo, (double)x * (double)x); }
+__device__ __forceinline__ void acc_sq(AccC& a, cplxf x) {
+  dd_add(a.rh, a.rl, (double)x.re * (double)x.re);
+  dd_add(a.rh, a.rl, (double)x.im * (double)x.im);
+}
+__device__ __forceinline__ AccR add(AccR a, AccR b) {
   a.lo += b.lo;
   dd_add(a.hi, a.lo, b.hi);
   return a;
 }
-__device__ __forceinline__ Acc<cplx> add(Acc<cplx> a, Acc<cplx> b) {
+__device__ __forceinline__ AccC add(AccC a, AccC b) {
   a.rl += b.rl;
   dd_add(a.rh, a.rl, b.rh);
   a.il += b.il;
   dd_add(a.ih, a.il, b.ih);
   return a;
 }
-__device__ __forceinline__ Acc<double> shfl_down(Acc<double> v, int d) {
-  return Acc<double>{__shfl_down_sync(0xffffffffu, v.hi, d), __shfl_down_sync(0xffffffffu, v.lo, d)};
+__device__ __forceinline__ AccR shfl_down(AccR v, int d) {
+  return AccR{__shfl_down_sync(0xffffffffu, v.hi, d), __shfl_down_sync(0xffffffffu, v.lo, d)};
 }
-__device__ __forceinline__ Acc<cplx> shfl_down(Acc<cplx> v, int d) {
-  return Acc<cplx>{__shfl_down_sync(0xffffffffu, v.rh, d), __shfl_down_sync(0xffffffffu, v.rl, d),
-                   __shfl_down_sync(0xffffffffu, v.ih, d), __shfl_down_sync(0xffffffffu, v.il, d)};
+__device__ __forceinline__ AccC shfl_down(AccC v, int d) {
+  return AccC{__shfl_down_sync(0xffffffffu, v.rh, d), __shfl_down_sync(0xffffffffu, v.rl, d),
+              __shfl_down_sync(0xffffffffu, v.ih, d), __shfl_down_sync(0xffffffffu, v.il, d)};
 }
 // the four (hi, lo) pairs a reduction point carries: slot 0 (re, im), slot 1 (re, im)
-__device__ __forceinline__ void acc_store(const Acc<double>& a, double* dd4) {
+__device__ __forceinline__ void acc_store(const AccR& a, double* dd4) {
   dd4[0] = a.hi;
   dd4[1] = a.lo;
   dd4[2] = 0.0;
   dd4[3] = 0.0;
 }
-__device__ __forceinline__ void acc_store(const Acc<cplx>& a, double* dd4) {
+__device__ __forceinline__ void acc_store(const AccC& a, double* dd4) {
   dd4[0] = a.rh;
   dd4[1] = a.rl;
   dd4[2] = a.ih;

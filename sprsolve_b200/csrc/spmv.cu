@@ -46,6 +46,16 @@ __device__ __forceinline__ cplx ld_x(const cplx* p, uint64_t pol) {
   asm("ld.global.nc.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;" : "=d"(v.re), "=d"(v.im) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ float ld_x(const float* p, uint64_t pol) {
+  float v;
+  asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ cplxf ld_x(const cplxf* p, uint64_t pol) {
+  cplxf v;
+  asm("ld.global.nc.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;" : "=f"(v.re), "=f"(v.im) : "l"(p), "l"(pol));
+  return v;
+}
 
 template <typename T, typename IP>
 struct SpmvArgs {
@@ -454,7 +464,8 @@ static void build_dict_impl(CsrMat<T>* m) {
   // Measured (profiles/r01_spmv_dict.txt): pays when the column stream is a third of the bytes and
   // rows are long (27-point f64: 1.24x); 7-point rows and complex values (4 of 20 bytes) gain
   // nothing -- their kernels are bound by the x gathers -- so they keep the plain stream.
-  if (!(e && *e == '1') && (sizeof(T) != 8 || (double)m->nnz < 12.0 * (double)n)) return;
+  // (f32: 4 of 8 bytes per non-zero are column indices, Complex32: 4 of 12 -- the same or a better ratio)
+  if (!(e && *e == '1') && (sizeof(T) > 8 || (double)m->nnz < 12.0 * (double)n)) return;
   const int w = ((int)m->max_row + 7) & ~7;  // 8 offsets = two 16-byte loads per gather batch
   DevBuf keys, keys2, rows, rows2, head, run, tmp, bad;
   keys.alloc(8 * (size_t)n);
@@ -777,5 +788,7 @@ CsrMat<T>::~CsrMat() {
 
 template struct CsrMat<double>;
 template struct CsrMat<cplx>;
+template struct CsrMat<float>;
+template struct CsrMat<cplxf>;
 
 }  // namespace spb

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kVecThreads) vec_scale_k(int64_t n, T a, T* x)
   SPB_GRID_STRIDE(i, n) x[i] = mul(x[i], a);  // vecalg.rs:593-595
 }
 template <typename T>
-__global__ void __launch_bounds__(kVecThreads) vec_rscale_k(int64_t n, double a, T* x) {
+__global__ void __launch_bounds__(kVecThreads) vec_rscale_k(int64_t n, real_t<T> a, T* x) {
   SPB_GRID_STRIDE(i, n) x[i] = mul_real(x[i], a);  // vecalg.rs:597-599
 }
 template <typename T>
@@ -96,7 +96,7 @@ void vec_scale(Ctx* c, int64_t n, T a, T* x) {
   SPB_VEC_LAUNCH(vec_scale_k<T>, n, a, x);
 }
 template <typename T>
-void vec_rscale(Ctx* c, int64_t n, double a, T* x) {
+void vec_rscale(Ctx* c, int64_t n, real_t<T> a, T* x) {
   SPB_VEC_LAUNCH(vec_rscale_k<T>, n, a, x);
 }
 template <typename T>
@@ -116,10 +116,12 @@ void vec_zero(Ctx* c, int64_t n, T* x) {
   template void vec_axpy<T>(Ctx*, int64_t, T, const T*, T*);                                 \
   template void vec_axpby<T>(Ctx*, int64_t, T, const T*, T, T*);                             \
   template void vec_scale<T>(Ctx*, int64_t, T, T*);                                          \
-  template void vec_rscale<T>(Ctx*, int64_t, double, T*);                                    \
+  template void vec_rscale<T>(Ctx*, int64_t, real_t<T>, T*);                                 \
   template void vec_conj<T>(Ctx*, int64_t, const T*, T*);                                    \
   template void vec_zero<T>(Ctx*, int64_t, T*);
 SPB_INST(double)
 SPB_INST(cplx)
+SPB_INST(float)
+SPB_INST(cplxf)
 
 }  // namespace spb

@@ -53,7 +53,7 @@ void vec_axpby(Ctx* c, int64_t n, T a, const T* x, T b, T* y);
 template <typename T>
 void vec_scale(Ctx* c, int64_t n, T a, T* x);
 template <typename T>
-void vec_rscale(Ctx* c, int64_t n, double a, T* x);
+void vec_rscale(Ctx* c, int64_t n, real_t<T> a, T* x);
 template <typename T>
 void vec_conj(Ctx* c, int64_t n, const T* x, T* out);
 template <typename T>

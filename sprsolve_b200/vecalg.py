@@ -10,7 +10,11 @@ from .api import _check, _dtype_code, _ptr, default_context
 
 
 def _prep(*arrs):
-    dt = np.complex128 if any(np.iscomplexobj(a) for a in arrs) else np.float64
+    """Common scalar type of the operands: f32 / Complex32 only when every operand is single precision."""
+    arrs = [np.asarray(a) for a in arrs]
+    single = all(a.dtype in (np.float32, np.complex64) for a in arrs)
+    cplx = any(np.iscomplexobj(a) for a in arrs)
+    dt = (np.complex64 if single else np.complex128) if cplx else (np.float32 if single else np.float64)
     return dt, [np.ascontiguousarray(a, dtype=dt) for a in arrs]
 
 
@@ -21,12 +25,20 @@ def _pair(a):
 
 def _out_inplace(y, dt):
     if not (isinstance(y, np.ndarray) and y.dtype == dt and y.flags.c_contiguous):
-        raise TypeError("in/out vector must be a contiguous float64/complex128 numpy array")
+        raise TypeError(f"in/out vector must be a contiguous {np.dtype(dt)} numpy array")
     return y
 
 
+def _io_dtype(vec):
+    """Scalar type of an in/out vector: its own if it is one of the four, else f64 / Complex64."""
+    d = getattr(vec, "dtype", None)
+    if d in (np.float32, np.complex64, np.float64, np.complex128):
+        return np.dtype(d).type
+    return np.complex128 if np.iscomplexobj(vec) else np.float64
+
+
 def _scalar(out, dt):
-    return complex(out[0], out[1]) if dt == np.complex128 else float(out[0])
+    return complex(out[0], out[1]) if np.dtype(dt).kind == "c" else float(out[0])
 
 
 def _h(ctx):
@@ -59,19 +71,19 @@ def norm2(x, ctx=None) -> float:
 
 
 def scale(a, vec, ctx=None) -> None:
-    dt = np.complex128 if np.iscomplexobj(vec) else np.float64
+    dt = _io_dtype(vec)
     _out_inplace(vec, dt)
     _check(F.lib().spb_vec_scale(_h(ctx), _dtype_code(dt), vec.size, _pair(a), _ptr(vec)))
 
 
 def rscale(a: float, vec, ctx=None) -> None:
-    dt = np.complex128 if np.iscomplexobj(vec) else np.float64
+    dt = _io_dtype(vec)
     _out_inplace(vec, dt)
     _check(F.lib().spb_vec_rscale(_h(ctx), _dtype_code(dt), vec.size, float(a), _ptr(vec)))
 
 
 def conj(vec_in, vec_out, ctx=None) -> None:
-    dt = np.complex128 if np.iscomplexobj(vec_out) else np.float64
+    dt = _io_dtype(vec_out)
     _out_inplace(vec_out, dt)
     x = np.ascontiguousarray(vec_in, dtype=dt)
     assert x.size == vec_out.size
@@ -80,7 +92,7 @@ def conj(vec_in, vec_out, ctx=None) -> None:
 
 def axpy(a, vec1, vec2, ctx=None) -> None:
     """vec2 += a * vec1 (src/vecalg.rs:104-116)."""
-    dt = np.complex128 if np.iscomplexobj(vec2) else np.float64
+    dt = _io_dtype(vec2)
     _out_inplace(vec2, dt)
     x = np.ascontiguousarray(vec1, dtype=dt)
     assert x.size == vec2.size
@@ -89,7 +101,7 @@ def axpy(a, vec1, vec2, ctx=None) -> None:
 
 def axpby(a, vec1, b, vec2, ctx=None) -> None:
     """vec2 = a * vec1 + b * vec2 (src/vecalg.rs:118-144)."""
-    dt = np.complex128 if np.iscomplexobj(vec2) else np.float64
+    dt = _io_dtype(vec2)
     _out_inplace(vec2, dt)
     x = np.ascontiguousarray(vec1, dtype=dt)
     assert x.size == vec2.size

@@ -133,13 +133,17 @@ def test_history_bit_for_bit_live(sp, exact, case, monkeypatch):
 def test_gauss_seidel_solver_bit_for_bit(sp, exact):
     """GaussSeidel::solve (src/gauss_seidel.rs:33-140): the sweeps are bit-exact and the per-sweep
     residual norm / the b-norm are exactly rounded on both sides."""
-    for A, rhs, its, eps in ((*exact.gen_dirichlet2d(24), 400, 1e-9), (*_ones_rhs(exact, exact.gen_convdiff27(10, 9, 8)), 200, 1e-10)):
+    for A, rhs, its, eps in ((*exact.gen_dirichlet2d(12), 2000, 1e-9), (*exact.gen_dirichlet2d(24), 300, 1e-9),
+                             (*_ones_rhs(exact, exact.gen_convdiff27(10, 9, 8)), 200, 1e-10)):
         G = sp.GpuCsrMat.new(A.indptr, A.indices, A.data)
         S = sp.GaussSeidel(G).record_history(its)
         x = np.zeros(A.n)
-        it, res = S.solve(rhs, x, its, eps)
         o = exact.gauss_seidel(A, rhs, max_iter=its, eps=eps, hist_cap=its)
-        assert o.status == 0 and (it, res) == (o.iters, o.resid)
+        try:
+            it, res = S.solve(rhs, x, its, eps)
+            assert o.status == 0 and (it, res) == (o.iters, o.resid)
+        except sp.InsufficientIterNum as e:
+            assert o.status == 3 and e.max_iter == its
         assert np.array_equal(S.history, o.hist) and np.array_equal(x, o.x)
 
 
