@@ -162,6 +162,13 @@ int spb_diag_precond_from_csr(spb_op* mat, spb_op** out);
  * n-1..0.  Sequential update order preserved (thread-per-row accumulation in CSR order).
  * SPB_ZERO_DIAGONAL like src/gauss_seidel.rs:72-78.  Single-GPU only. */
 int spb_gs_precond_create(spb_op* mat, int mode, spb_op** out);
+/* Relaxed variant (the reference has no relaxation): every update of the
+ * sweep becomes x_i <- (1 - omega) x_i + omega g_i, g_i the src/gauss_seidel.rs:123 value, 0 < omega < 2.
+ * FORWARD: one SOR sweep from z = 0; SYMMETRIC: SSOR(omega) = omega (2 - omega) (D + omega U)^-1 D
+ * (D + omega L)^-1, symmetric positive definite whenever A is symmetric with D > 0 (a valid MINRES
+ * preconditioner, src/minres.rs:176).  omega == 1 is spb_gs_precond_create.  Sequential update order
+ * preserved (level-scheduled kernel).  Single-GPU only. */
+int spb_gs_precond_create_relaxed(spb_op* mat, int mode, double omega, spb_op** out);
 int spb_gs_levels(spb_op* gs, int64_t* n_levels_fwd, int64_t* n_levels_bwd);
 /* Block-wavefront schedule of the sweep (diagnostics): info = {fwd ok, rows per block, blocks, fwd chunks,
  * fwd local levels (max over blocks), ring stages, shared memory bytes, bwd ok, bwd chunks, bwd local levels,
@@ -190,6 +197,9 @@ int spb_bicgstab_create(spb_op* A, int64_t size, spb_solver** out);
 int spb_minres_create(spb_op* A, int64_t size, spb_solver** out);
 int spb_csminres_create(spb_op* A, int64_t size, spb_solver** out);
 int spb_gauss_seidel_create(spb_op* A, spb_solver** out);
+/* The same stationary solver with successive over-relaxation (SOR), 0 < omega < 2; omega == 1 is
+ * GaussSeidel::solve itself. */
+int spb_gauss_seidel_create_relaxed(spb_op* A, double omega, spb_solver** out);
 /* solve / precond_solve (src/bicg_stab.rs:35,204; src/minres.rs:31,178; src/cs_minres.rs:29;
  * src/gauss_seidel.rs:33).  precond == NULL selects `solve`.  x is in/out (initial guess).
  * On SPB_OK: *iters, *resid as the reference's Ok((iters, resid)).  hist (optional): see

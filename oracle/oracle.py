@@ -20,7 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 OK, INCOMPATIBLE_FORMAT, ZERO_DIAGONAL, INSUFFICIENT_ITER, BREAKDOWN, INVALID_PRECOND = range(6)
-PC_NONE, PC_DIAG, PC_DIAG_REAL, PC_GS_FWD, PC_GS_SYM = range(5)
+PC_NONE, PC_DIAG, PC_DIAG_REAL, PC_GS_FWD, PC_GS_SYM, PC_SOR_FWD, PC_SSOR = range(7)
 
 _lib = None
 
@@ -319,9 +319,17 @@ def diag_apply(diag, v) -> np.ndarray:
     return out
 
 
-def gs_apply(A: Csr, v, symmetric: bool) -> np.ndarray:
+def gs_apply(A: Csr, v, symmetric: bool, omega: float = 1.0) -> np.ndarray:
+    """Gauss-Seidel operator; omega != 1: relaxed sweep (symmetric: SSOR(omega)), see sprs_oracle.h."""
     v = np.ascontiguousarray(v, dtype=A.dtype)
     out = np.empty_like(v)
+    if omega != 1.0:
+        st = getattr(lib(), f"orc_sor_apply_{_sfx(A.dtype)}")(
+            _i64(A.n), _ptr(A.indptr), _ptr(A.indices), _ptr(A.data), C.c_int(int(symmetric)), _dbl(omega), _ptr(v), _ptr(out)
+        )
+        if st != OK:
+            raise ZeroDivisionError("zero diagonal")
+        return out
     st = getattr(lib(), f"orc_gs_apply_{_sfx(A.dtype)}")(
         _i64(A.n), _ptr(A.indptr), _ptr(A.indices), _ptr(A.data), C.c_int(int(symmetric)), _ptr(v), _ptr(out)
     )
@@ -341,7 +349,7 @@ class SolveOut:
 
 
 def _pc_args(A: Csr, pc):
-    """pc: None | ("diag", array) | ("gs_fwd",) | ("gs_sym",)."""
+    """pc: None | ("diag", array) | ("gs_fwd",) | ("gs_sym",) | ("sor_fwd", omega) | ("ssor", omega)."""
     if pc is None:
         return PC_NONE, None
     kind = pc[0]
@@ -354,6 +362,8 @@ def _pc_args(A: Csr, pc):
         return PC_GS_FWD, None
     if kind == "gs_sym":
         return PC_GS_SYM, None
+    if kind in ("sor_fwd", "ssor"):
+        return (PC_SOR_FWD if kind == "sor_fwd" else PC_SSOR), np.array([pc[1]], dtype=_real_dtype(A.dtype))
     raise ValueError(kind)
 
 
@@ -393,13 +403,20 @@ def csminres(A, rhs, x0=None, max_iter=1000, tol=1e-8, work=None, size=None, his
     return _solve("csminres", 7, A, rhs, x0, max_iter, tol, None, work, size, hist_cap, with_pc=False)
 
 
-def gauss_seidel(A: Csr, rhs, x0=None, max_iter=300, eps=0.0, work=None, is_csr=True, hist_cap=4096):
+def gauss_seidel(A: Csr, rhs, x0=None, max_iter=300, eps=0.0, work=None, is_csr=True, hist_cap=4096, omega=1.0):
     rhs = np.ascontiguousarray(rhs, dtype=A.dtype)
     x = np.array(x0, dtype=A.dtype, copy=True) if x0 is not None else np.zeros(rhs.size, dtype=A.dtype)
     if work is None:
         work = np.zeros(2 * A.n, dtype=A.dtype)
     hist = np.zeros(hist_cap, dtype=np.float64)
     iters, resid, hlen = _i64(0), _dbl(0.0), _i64(0)
+    if omega != 1.0:  # SOR: GaussSeidel::solve with the relaxed update (sprs_oracle.h)
+        st = getattr(lib(), f"orc_sor_solve_{_sfx(A.dtype)}")(
+            _i64(A.n), _i64(A.ncols), C.c_int(int(is_csr)), _i64(rhs.size), _i64(x.size), _ptr(A.indptr),
+            _ptr(A.indices), _ptr(A.data), _ptr(rhs), _ptr(x), _i64(max_iter), _dbl(eps), _dbl(omega), _ptr(work),
+            C.byref(iters), C.byref(resid), _ptr(hist), _i64(hist_cap), C.byref(hlen),
+        )
+        return SolveOut(int(st), int(iters.value), float(resid.value), x, hist[: min(hlen.value, hist_cap)].copy())
     st = getattr(lib(), f"orc_gauss_seidel_{_sfx(A.dtype)}")(
         _i64(A.n), _i64(A.ncols), C.c_int(int(is_csr)), _i64(rhs.size), _i64(x.size), _ptr(A.indptr),
         _ptr(A.indices), _ptr(A.data), _ptr(rhs), _ptr(x), _i64(max_iter), _dbl(eps), _ptr(work),

@@ -531,14 +531,25 @@ struct Precond {
   T* gs_tmp;           // GS_SYM: forward result
   const Levels* lev_f; // modes >= 1: level schedules of the lower / upper pattern
   const Levels* lev_b;
-  void level_sweep(const Levels& L, const T* rhs, const T* lo, const T* hi, T* out) const {
+  real_t<T> omega;     // SOR / SSOR kinds: relaxation factor
+  // Relaxed update (SOR): x_i <- (1 - omega) x_i + omega * g_i, g_i the Gauss-Seidel value of
+  // gauss_seidel.rs:123.  The reference has no relaxation; this fixes the operation order for it:
+  // two real-by-scalar products, one add.  omega == 1 never takes this path (plain sweep, same bits as before).
+  inline T relax(T xold, T g) const {
+    const real_t<T> one_m = real_t<T>(1) - omega;
+    return add(mul_real(xold, one_m), mul_real(g, omega));
+  }
+  // xold: the value x_i is relaxed against (null: 0, a sweep from zero; unused when omega == 1)
+  void level_sweep(const Levels& L, const T* rhs, const T* lo, const T* hi, T* out, const T* xold = nullptr,
+                   bool relaxed = false) const {
     const int64_t nl = (int64_t)L.ptr.size() - 1;
     for (int64_t l = 0; l < nl; ++l) {
       const int64_t b = L.ptr[l], e = L.ptr[l + 1];
 #pragma omp parallel for schedule(static) if (e - b > 2048)
       for (int64_t i = b; i < e; ++i) {
         const int64_t r = L.rows[i];
-        out[r] = gs_row_split(*A, r, rhs[r], gs_diag[r], lo, hi);
+        const T g = gs_row_split(*A, r, rhs[r], gs_diag[r], lo, hi);
+        out[r] = relaxed ? relax(xold ? xold[r] : zero_of(T()), g) : g;
       }
     }
   }
@@ -570,6 +581,27 @@ struct Precond {
         for (int64_t r = 0; r < n; ++r) out[r] = gs_row(*A, r, in[r], gs_diag[r], out);
         for (int64_t r = n - 1; r >= 0; --r) out[r] = gs_row(*A, r, in[r], gs_diag[r], out);
         break;
+      case ORC_PC_SOR_FWD:
+        // relaxed forward sweep from zero: z_i = (1 - w) * 0 + w * g_i
+        if (lev_f) {
+          level_sweep(*lev_f, in, out, nullptr, out, nullptr, true);
+          break;
+        }
+        zero_vec(n, out);
+        for (int64_t r = 0; r < n; ++r) out[r] = relax(out[r], gs_row(*A, r, in[r], gs_diag[r], out));
+        break;
+      case ORC_PC_SSOR:
+        // SSOR(w): relaxed forward sweep from zero, then the relaxed sweep over rows n-1..0 in place:
+        // z = w (2 - w) (D + w U)^-1 D (D + w L)^-1 r, symmetric positive definite for 0 < w < 2, D > 0.
+        if (lev_f && lev_b) {
+          level_sweep(*lev_f, in, gs_tmp, nullptr, gs_tmp, nullptr, true);
+          level_sweep(*lev_b, in, gs_tmp, out, out, gs_tmp, true);
+          break;
+        }
+        zero_vec(n, out);
+        for (int64_t r = 0; r < n; ++r) out[r] = relax(out[r], gs_row(*A, r, in[r], gs_diag[r], out));
+        for (int64_t r = n - 1; r >= 0; --r) out[r] = relax(out[r], gs_row(*A, r, in[r], gs_diag[r], out));
+        break;
       default:
         copy_vec(n, in, out);
     }
@@ -589,8 +621,13 @@ struct PrecondOwner {
     p.gs_tmp = nullptr;
     p.lev_f = nullptr;
     p.lev_b = nullptr;
+    p.omega = real_t<T>(1);
     ok = true;
     bad_row = -1;
+    if (kind == ORC_PC_SOR_FWD || kind == ORC_PC_SSOR) {
+      p.omega = *reinterpret_cast<const real_t<T>*>(data);
+      if (p.omega == real_t<T>(1)) p.kind = kind = (kind == ORC_PC_SSOR ? ORC_PC_GS_SYM : ORC_PC_GS_FWD);
+    }
     if (kind == ORC_PC_DIAG) {
       // precond.rs:20-24: diag_inv.push(V::one() / *v)
       p.dinv_t = new T[n];
@@ -600,14 +637,14 @@ struct PrecondOwner {
       p.dinv_r = new real_t<T>[n];
       const real_t<T>* d = reinterpret_cast<const real_t<T>*>(data);
       for (int64_t i = 0; i < n; ++i) p.dinv_r[i] = real_t<T>(1) / d[i];
-    } else if (kind == ORC_PC_GS_FWD || kind == ORC_PC_GS_SYM) {
+    } else if (kind == ORC_PC_GS_FWD || kind == ORC_PC_GS_SYM || kind == ORC_PC_SOR_FWD || kind == ORC_PC_SSOR) {
       p.gs_diag = new T[n];
       bad_row = gs_diagonals(*A, p.gs_diag);
       ok = bad_row < 0;
       if (ok && g_mode >= 1) {
         lev_f.build(*A, true);
         p.lev_f = &lev_f;
-        if (kind == ORC_PC_GS_SYM) {
+        if (kind == ORC_PC_GS_SYM || kind == ORC_PC_SSOR) {
           lev_b.build(*A, false);
           p.lev_b = &lev_b;
           p.gs_tmp = new T[n];
@@ -875,9 +912,14 @@ int minres(int64_t size, int64_t n_rhs, int64_t n_x, const Csr<T>& A, const Prec
 template <typename T>
 int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x,
                  const Csr<T>& A, const T* rhs, T* x, int64_t max_iter, double eps, T* ws,
-                 int64_t* iters, double* resid, Hist& h) {
+                 int64_t* iters, double* resid, Hist& h, double omega_d = 1.0) {
   using R = real_t<T>;
   const R EPS_T = eps_of<T>();
+  // omega != 1: successive over-relaxation, x_i <- (1 - w) x_i + w g_i (not in the reference; same
+  // update as Precond::relax); omega == 1 is the reference's loop, untouched.
+  const R omega = (R)omega_d, one_m = R(1) - omega;
+  const bool relaxed = omega != R(1);
+  auto upd = [&](T xold, T g) { return relaxed ? add(mul_real(xold, one_m), mul_real(g, omega)) : g; };
   if (nrows != ncols) return ORC_INCOMPATIBLE_FORMAT;  // :16-20 (GaussSeidel::new)
   if (!is_csr) return ORC_INCOMPATIBLE_FORMAT;         // :22-26
   if (n_rhs != nrows) return ORC_INCOMPATIBLE_FORMAT;  // :41-45
@@ -909,7 +951,7 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
     }
     diag[row] = d;                              // :81
     b_norm += square(rhs[row]);                 // :83
-    x[row] = divi(sub(rhs[row], sigma), d);     // :84
+    x[row] = upd(x[row], divi(sub(rhs[row], sigma), d));  // :84
   }
   if (g_mode == 3) b_norm = exact_sumsq(n, rhs);  // exact-dot flavour: the same sum, rounded once
   const R tol2 = (R)eps * std::sqrt(b_norm);  // :87
@@ -923,7 +965,7 @@ int gauss_seidel(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_
     return ORC_OK;
   }
   for (int64_t it = 1; it < max_iter; ++it) {   // :110
-    for (int64_t row = 0; row < n; ++row) x[row] = gs_row(A, row, rhs[row], diag[row], x);
+    for (int64_t row = 0; row < n; ++row) x[row] = upd(x[row], gs_row(A, row, rhs[row], diag[row], x));
     A.mul_vec(x, res);                          // :128
     axpy(n, neg(one_of(T())), rhs, res);        // :131
     rn = norm2(n, res);                         // :133
@@ -999,23 +1041,24 @@ template <typename T>
 int run_gs(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x,
            const int64_t* indptr, const int32_t* idx, const void* a, const void* rhs,
            void* x, int64_t max_iter, double eps, void* work, int64_t* iters, double* resid,
-           double* hist, int64_t hist_cap, int64_t* hist_len) {
+           double* hist, int64_t hist_cap, int64_t* hist_len, double omega = 1.0) {
   Csr<T> A{nrows, indptr, idx, reinterpret_cast<const T*>(a)};
   Hist h{hist, hist_cap, 0};
   *iters = 0;
   *resid = 0.0;
   int st = gauss_seidel<T>(nrows, ncols, is_csr, n_rhs, n_x, A, reinterpret_cast<const T*>(rhs),
                            reinterpret_cast<T*>(x), max_iter, eps, reinterpret_cast<T*>(work),
-                           iters, resid, h);
+                           iters, resid, h, omega);
   if (hist_len) *hist_len = h.len;
   return st;
 }
 
 template <typename T>
 int run_gs_apply(int64_t n, const int64_t* indptr, const int32_t* idx, const void* a,
-                 int symmetric, const void* in, void* out) {
+                 int symmetric, const void* in, void* out, double omega = 1.0) {
   Csr<T> A{n, indptr, idx, reinterpret_cast<const T*>(a)};
-  PrecondOwner<T> po(symmetric ? ORC_PC_GS_SYM : ORC_PC_GS_FWD, n, &A, nullptr);
+  const real_t<T> w = (real_t<T>)omega;
+  PrecondOwner<T> po(symmetric ? ORC_PC_SSOR : ORC_PC_SOR_FWD, n, &A, &w);
   if (!po.ok) return ORC_ZERO_DIAGONAL;
   po.p.apply(reinterpret_cast<const T*>(in), reinterpret_cast<T*>(out));
   return ORC_OK;
@@ -1347,6 +1390,24 @@ int orc_gauss_seidel_c(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, 
   return run_gs<cplxf>(nrows, ncols, is_csr, n_rhs, n_x, indptr, idx, a, rhs, x, max_iter, eps, work, iters, resid, hist,
                        hist_cap, hist_len);
 }
+
+// ---------- relaxed Gauss-Seidel (SOR / SSOR(w)): build-side additions, see sprs_oracle.h ----------
+#define ORC_SOR_APPLY(sfx, T, F)                                                                                     \
+  int orc_sor_apply_##sfx(int64_t n, const int64_t* ip, const int32_t* idx, const F* a, int sym, double omega,      \
+                          const F* in, F* out) {                                                                    \
+    return run_gs_apply<T>(n, ip, idx, a, sym, in, out, omega);                                                     \
+  }                                                                                                                  \
+  int orc_sor_solve_##sfx(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x, const int64_t* ip,   \
+                          const int32_t* idx, const F* a, const F* rhs, F* x, int64_t max_iter, double eps,          \
+                          double omega, F* work, int64_t* iters, double* resid, double* hist, int64_t hist_cap,      \
+                          int64_t* hist_len) {                                                                       \
+    return run_gs<T>(nrows, ncols, is_csr, n_rhs, n_x, ip, idx, a, rhs, x, max_iter, eps, work, iters, resid, hist,  \
+                     hist_cap, hist_len, omega);                                                                     \
+  }
+ORC_SOR_APPLY(d, double, double)
+ORC_SOR_APPLY(z, cplx, double)
+ORC_SOR_APPLY(s, float, float)
+ORC_SOR_APPLY(c, cplxf, float)
 
 // ---------- generators ----------------------------------------------------------------------
 static inline bool is_border(int64_t r, int64_t c, int64_t rows, int64_t cols) {

@@ -41,7 +41,12 @@ enum {
   ORC_PC_DIAG = 1,      /* DiagPrecond<T,T>: pc_data = diag (T), n entries (precond.rs:20-29) */
   ORC_PC_DIAG_REAL = 2, /* DiagPrecond<Complex,f64>: pc_data = real diag, n entries */
   ORC_PC_GS_FWD = 3,    /* z = one forward gauss_seidel.rs:111-125 sweep from z=0, rhs=r */
-  ORC_PC_GS_SYM = 4     /* forward sweep from 0 then the same body over rows n-1..0 */
+  ORC_PC_GS_SYM = 4,    /* forward sweep from 0 then the same body over rows n-1..0 */
+  /* Relaxed variants (the reference has no relaxation, so the update is
+   * DEFINED here: x_i <- (1 - w) x_i + w g_i with g_i the gauss_seidel.rs:123 value, computed as
+   * mul_real(x_i, 1 - w) + mul_real(g_i, w)).  pc_data = &omega (one T::Real).  omega == 1 is GS_FWD / GS_SYM. */
+  ORC_PC_SOR_FWD = 5,   /* relaxed forward sweep from z = 0 */
+  ORC_PC_SSOR = 6       /* SSOR(w): relaxed forward sweep from 0, then the relaxed sweep over rows n-1..0 */
 };
 
 /* ---- SpMV: src/mat.rs:68-129 (CSR), :130-142 (CSC), :145-152 (mul_vec_dot) ---- */
@@ -165,6 +170,20 @@ int64_t orc_gen_lap3d7_z(int64_t nx, int64_t ny, int64_t nz, double shift_re, do
 int64_t orc_gen_convdiff27_d(int64_t nx, int64_t ny, int64_t nz, double bx, double by, double bz,
                              int64_t row_begin, int64_t row_end, int64_t* indptr, int32_t* idx,
                              double* a);
+
+/* Relaxed Gauss-Seidel operator (symmetric: SSOR(omega)) and the stationary SOR solver (GaussSeidel::solve
+ * with the relaxed update; same returns).  Suffixes d / z / s / c; complex arrays interleaved. */
+#define ORC_SOR_DECL(sfx, F)                                                                                          \
+  int orc_sor_apply_##sfx(int64_t n, const int64_t* indptr, const int32_t* idx, const F* a, int symmetric,           \
+                          double omega, const F* in, F* out);                                                         \
+  int orc_sor_solve_##sfx(int64_t nrows, int64_t ncols, int is_csr, int64_t n_rhs, int64_t n_x,                       \
+                          const int64_t* indptr, const int32_t* idx, const F* a, const F* rhs, F* x, int64_t max_iter, \
+                          double eps, double omega, F* work, int64_t* iters, double* resid, double* hist,             \
+                          int64_t hist_cap, int64_t* hist_len);
+ORC_SOR_DECL(d, double)
+ORC_SOR_DECL(z, double)
+ORC_SOR_DECL(s, float)
+ORC_SOR_DECL(c, float)
 
 int orc_max_threads(void);
 void orc_set_threads(int n);

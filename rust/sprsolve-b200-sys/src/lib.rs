@@ -6,7 +6,7 @@
 #![allow(non_snake_case, non_camel_case_types, clippy::many_single_char_names)]
 
 use cauchy::Scalar;
-use num_complex::Complex64;
+use num_complex::{Complex32, Complex64};
 use sprs::CsMatI;
 use sprsolve::error::{SolveResult, SolverError};
 use sprsolve::MatVecMul;
@@ -38,6 +38,8 @@ pub const SPB_DIM_MISMATCH: c_int = 6;
 pub const SPB_UNIMPLEMENTED: c_int = 7;
 pub const SPB_F64: c_int = 0;
 pub const SPB_C128: c_int = 1;
+pub const SPB_F32: c_int = 2;
+pub const SPB_C64: c_int = 3;
 pub const SPB_GS_FORWARD: c_int = 0;
 pub const SPB_GS_SYMMETRIC: c_int = 1;
 
@@ -72,10 +74,12 @@ extern "C" {
         ctx: *mut spb_ctx, dtype: c_int, diag_dtype: c_int, diag: *const c_void, n: i64, out: *mut *mut spb_op,
     ) -> c_int;
     pub fn spb_gs_precond_create(mat: *mut spb_op, mode: c_int, out: *mut *mut spb_op) -> c_int;
+    pub fn spb_gs_precond_create_relaxed(mat: *mut spb_op, mode: c_int, omega: c_double, out: *mut *mut spb_op) -> c_int;
     pub fn spb_bicgstab_create(A: *mut spb_op, size: i64, out: *mut *mut spb_solver) -> c_int;
     pub fn spb_minres_create(A: *mut spb_op, size: i64, out: *mut *mut spb_solver) -> c_int;
     pub fn spb_csminres_create(A: *mut spb_op, size: i64, out: *mut *mut spb_solver) -> c_int;
     pub fn spb_gauss_seidel_create(A: *mut spb_op, out: *mut *mut spb_solver) -> c_int;
+    pub fn spb_gauss_seidel_create_relaxed(A: *mut spb_op, omega: c_double, out: *mut *mut spb_solver) -> c_int;
     pub fn spb_solver_solve(
         s: *mut spb_solver, precond: *mut spb_op, rhs: *const c_void, n_rhs: i64, x: *mut c_void, n_x: i64,
         max_iter: i64, tol: c_double, iters: *mut i64, resid: *mut c_double, hist: *mut c_double, hist_cap: i64,
@@ -89,20 +93,66 @@ fn last_error() -> String {
 }
 
 /// The instantiated scalar types: `f64` and `Complex64` (SURVEY.md section 8f lists f32/c32 as next).
-pub trait GpuScalar: Scalar<Real = f64> {
+/// The four `cauchy::Scalar` types the reference is generic over (it dispatches s / d / c / z,
+/// src/mkl_mat.rs:68-71).  Scalars cross the C ABI as doubles; for the f32 types they hold floats.
+pub trait GpuScalar: Scalar {
     const DTYPE: c_int;
+    /// dtype code of `Self::Real` (a real diagonal for a complex system, `DiagPrecond<T, T::Real>`)
+    const REAL_DTYPE: c_int;
     fn from_pair(p: [f64; 2]) -> Self;
+    fn real_to_f64(r: Self::Real) -> f64;
+    fn real_from_f64(v: f64) -> Self::Real;
 }
 impl GpuScalar for f64 {
     const DTYPE: c_int = SPB_F64;
+    const REAL_DTYPE: c_int = SPB_F64;
     fn from_pair(p: [f64; 2]) -> Self {
         p[0]
+    }
+    fn real_to_f64(r: f64) -> f64 {
+        r
+    }
+    fn real_from_f64(v: f64) -> f64 {
+        v
     }
 }
 impl GpuScalar for Complex64 {
     const DTYPE: c_int = SPB_C128;
+    const REAL_DTYPE: c_int = SPB_F64;
     fn from_pair(p: [f64; 2]) -> Self {
         Complex64::new(p[0], p[1])
+    }
+    fn real_to_f64(r: f64) -> f64 {
+        r
+    }
+    fn real_from_f64(v: f64) -> f64 {
+        v
+    }
+}
+impl GpuScalar for f32 {
+    const DTYPE: c_int = SPB_F32;
+    const REAL_DTYPE: c_int = SPB_F32;
+    fn from_pair(p: [f64; 2]) -> Self {
+        p[0] as f32
+    }
+    fn real_to_f64(r: f32) -> f64 {
+        r as f64
+    }
+    fn real_from_f64(v: f64) -> f32 {
+        v as f32 // exact: the library hands back values already rounded to float
+    }
+}
+impl GpuScalar for Complex32 {
+    const DTYPE: c_int = SPB_C64;
+    const REAL_DTYPE: c_int = SPB_F32;
+    fn from_pair(p: [f64; 2]) -> Self {
+        Complex32::new(p[0] as f32, p[1] as f32)
+    }
+    fn real_to_f64(r: f32) -> f64 {
+        r as f64
+    }
+    fn real_from_f64(v: f64) -> f32 {
+        v as f32
     }
 }
 
@@ -285,9 +335,13 @@ pub struct GpuGsPrecond<'c, T: GpuScalar> {
 }
 impl<'c, T: GpuScalar> GpuGsPrecond<'c, T> {
     pub fn new(A: &GpuCsrMat<'c, T>, symmetric: bool) -> SolveResult<Self> {
+        Self::new_relaxed(A, symmetric, 1.0)
+    }
+    /// Relaxed sweep, 0 < omega < 2 (forward: SOR sweep from zero; symmetric: SSOR(omega)).
+    pub fn new_relaxed(A: &GpuCsrMat<'c, T>, symmetric: bool, omega: f64) -> SolveResult<Self> {
         let mut h = std::ptr::null_mut();
         let mode = if symmetric { SPB_GS_SYMMETRIC } else { SPB_GS_FORWARD };
-        match unsafe { spb_gs_precond_create(A.h, mode, &mut h) } {
+        match unsafe { spb_gs_precond_create_relaxed(A.h, mode, omega, &mut h) } {
             SPB_OK => Ok(GpuGsPrecond { h, _ctx: PhantomData, _t: PhantomData }),
             SPB_ZERO_DIAGONAL => {
                 let msg = last_error();
@@ -326,7 +380,7 @@ impl<'c, T: GpuScalar> GpuOp for GpuGsPrecond<'c, T> {
 }
 
 // ------------------------------------------------------------------ solvers
-fn to_result<R: Copy>(st: c_int, iters: i64, resid: R) -> SolveResult<(usize, R)> {
+fn to_result<R>(st: c_int, iters: i64, resid: R) -> SolveResult<(usize, R)> {
     match st {
         SPB_OK => Ok((iters as usize, resid)),
         SPB_INCOMPATIBLE_FORMAT => Err(SolverError::IncompatibleMatrixFormat(last_error())),
@@ -354,18 +408,19 @@ macro_rules! gpu_solver {
                 assert_eq!(st, SPB_OK, "{}", last_error());
                 $name { h, _A: A }
             }
-            fn run(&mut self, pc: *mut spb_op, rhs: &[T], x: &mut [T], max_iter: usize, tol: f64)
-                   -> SolveResult<(usize, f64)> {
+            fn run(&mut self, pc: *mut spb_op, rhs: &[T], x: &mut [T], max_iter: usize, tol: T::Real)
+                   -> SolveResult<(usize, T::Real)> {
                 let (mut iters, mut resid) = (0i64, 0f64);
                 let st = unsafe {
                     spb_solver_solve(self.h, pc, rhs.as_ptr() as *const c_void, rhs.len() as i64,
-                                     x.as_mut_ptr() as *mut c_void, x.len() as i64, max_iter as i64, tol,
+                                     x.as_mut_ptr() as *mut c_void, x.len() as i64, max_iter as i64, T::real_to_f64(tol),
                                      &mut iters, &mut resid, std::ptr::null_mut(), 0, std::ptr::null_mut())
                 };
-                to_result(st, iters, resid)
+                to_result(st, iters, T::real_from_f64(resid))
             }
-            /// Solves Ax = b, without preconditioner.
-            pub fn solve(&mut self, rhs: &[T], x: &mut [T], max_iter: usize, tol: f64) -> SolveResult<(usize, f64)> {
+            /// Solves Ax = b, without preconditioner (the reference's `solve(&mut self, rhs, x, max_iter, tol: T::Real)
+            /// -> SolveResult<(usize, T::Real)>`, src/bicg_stab.rs:35-41).
+            pub fn solve(&mut self, rhs: &[T], x: &mut [T], max_iter: usize, tol: T::Real) -> SolveResult<(usize, T::Real)> {
                 self.run(std::ptr::null_mut(), rhs, x, max_iter, tol)
             }
             gpu_solver!(@pc $has_pc);
@@ -378,8 +433,8 @@ macro_rules! gpu_solver {
     };
     (@pc yes) => {
         /// Same as the reference's `precond_solve<P: MatVecMul<T>>`, for device-resident `P`.
-        pub fn precond_solve<P: GpuOp>(&mut self, precond: &P, rhs: &[T], x: &mut [T], max_iter: usize, tol: f64)
-                                       -> SolveResult<(usize, f64)> {
+        pub fn precond_solve<P: GpuOp>(&mut self, precond: &P, rhs: &[T], x: &mut [T], max_iter: usize, tol: T::Real)
+                                       -> SolveResult<(usize, T::Real)> {
             self.run(precond.raw(), rhs, x, max_iter, tol)
         }
     };
@@ -397,20 +452,24 @@ pub struct GpuGaussSeidel<'data, 'c, T: GpuScalar> {
 }
 impl<'data, 'c, T: GpuScalar> GpuGaussSeidel<'data, 'c, T> {
     pub fn new(A: &'data GpuCsrMat<'c, T>) -> SolveResult<Self> {
+        Self::new_relaxed(A, 1.0)
+    }
+    /// Successive over-relaxation, 0 < omega < 2 (omega = 1: the reference's solver).
+    pub fn new_relaxed(A: &'data GpuCsrMat<'c, T>, omega: f64) -> SolveResult<Self> {
         let mut h = std::ptr::null_mut();
-        match unsafe { spb_gauss_seidel_create(A.h, &mut h) } {
+        match unsafe { spb_gauss_seidel_create_relaxed(A.h, omega, &mut h) } {
             SPB_OK => Ok(GpuGaussSeidel { h, _A: A }),
             _ => Err(SolverError::IncompatibleMatrixFormat(last_error())),
         }
     }
-    pub fn solve(&mut self, rhs: &[T], x: &mut [T], max_iter: usize, eps: f64) -> SolveResult<(usize, f64)> {
+    pub fn solve(&mut self, rhs: &[T], x: &mut [T], max_iter: usize, eps: T::Real) -> SolveResult<(usize, T::Real)> {
         let (mut iters, mut resid) = (0i64, 0f64);
         let st = unsafe {
             spb_solver_solve(self.h, std::ptr::null_mut(), rhs.as_ptr() as *const c_void, rhs.len() as i64,
-                             x.as_mut_ptr() as *mut c_void, x.len() as i64, max_iter as i64, eps, &mut iters,
+                             x.as_mut_ptr() as *mut c_void, x.len() as i64, max_iter as i64, T::real_to_f64(eps), &mut iters,
                              &mut resid, std::ptr::null_mut(), 0, std::ptr::null_mut())
         };
-        to_result(st, iters, resid)
+        to_result(st, iters, T::real_from_f64(resid))
     }
 }
 impl<'data, 'c, T: GpuScalar> Drop for GpuGaussSeidel<'data, 'c, T> {

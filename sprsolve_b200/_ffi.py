@@ -71,6 +71,7 @@ SIGNATURES = {
     "spb_diag_precond_create": (C.c_int, [vp, C.c_int, C.c_int, vp, i64, pp]),
     "spb_diag_precond_from_csr": (C.c_int, [vp, pp]),
     "spb_gs_precond_create": (C.c_int, [vp, C.c_int, pp]),
+    "spb_gs_precond_create_relaxed": (C.c_int, [vp, C.c_int, dbl, pp]),
     "spb_gs_levels": (C.c_int, [vp, pi64, pi64]),
     "spb_gs_schedule_info": (C.c_int, [vp, pi64, pi64, i64]),
     "spb_vec_dot": (C.c_int, [vp, C.c_int, i64, vp, vp, pdbl]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "spb_minres_create": (C.c_int, [vp, i64, pp]),
     "spb_csminres_create": (C.c_int, [vp, i64, pp]),
     "spb_gauss_seidel_create": (C.c_int, [vp, pp]),
+    "spb_gauss_seidel_create_relaxed": (C.c_int, [vp, dbl, pp]),
     "spb_solver_solve": (C.c_int, [vp, vp, vp, i64, vp, i64, i64, dbl, pi64, pdbl, vp, i64, pi64]),
     "spb_solver_solve_dev": (C.c_int, [vp, vp, vp, vp, i64, dbl, pi64, pdbl, vp, i64, pi64]),
     "spb_solver_set_poll_interval": (C.c_int, [vp, C.c_int]),

@@ -420,14 +420,15 @@ class GaussSeidelPrecond(MatVecMul):
     """Level-scheduled Gauss-Seidel sweep as a MatVecMul operator (sweep body
     src/gauss_seidel.rs:111-125; the reference has no such wrapper -- see DESIGN.md)."""
 
-    def __init__(self, A: GpuCsrMat, symmetric: bool = False):
+    def __init__(self, A: GpuCsrMat, symmetric: bool = False, omega: float = 1.0):
+        """omega != 1: the relaxed sweep (SOR; symmetric: SSOR(omega)), spb_gs_precond_create_relaxed."""
         h = C.c_void_p()
-        st = F.lib().spb_gs_precond_create(A._h, F.GS_SYMMETRIC if symmetric else F.GS_FORWARD, C.byref(h))
+        st = F.lib().spb_gs_precond_create_relaxed(A._h, F.GS_SYMMETRIC if symmetric else F.GS_FORWARD, float(omega), C.byref(h))
         if st == F.ZERO_DIAGONAL:
             msg = F.last_error()
             raise ZeorDiagonalElem(int(msg.rsplit(" ", 1)[-1]))
         _check(st)
-        self._h, self.ctx, self.dtype, self._A = h, A.ctx, A.dtype, A
+        self._h, self.ctx, self.dtype, self._A, self.omega = h, A.ctx, A.dtype, A, float(omega)
 
     def levels(self):
         a, b = C.c_int64(0), C.c_int64(0)
@@ -552,6 +553,17 @@ class GaussSeidel(_Solver):
 
     _create = "spb_gauss_seidel_create"
     _needs_size = False
+
+    def __init__(self, A: MatVecMul, omega: float = 1.0):
+        """omega != 1: successive over-relaxation (spb_gauss_seidel_create_relaxed); 1: the reference's solver."""
+        if omega == 1.0:
+            super().__init__(A)
+            return
+        self.A, self.ctx, self.dtype = A, A.ctx, A.dtype
+        self.history, self.hist_cap = np.zeros(0), 0
+        h = C.c_void_p()
+        _check(F.lib().spb_gauss_seidel_create_relaxed(A._h, float(omega), C.byref(h)))
+        self._h = h
 
     def solve(self, rhs, x, max_iter: int, eps: float):
         return self._solve(None, rhs, x, max_iter, eps)

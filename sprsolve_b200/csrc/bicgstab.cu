@@ -245,6 +245,8 @@ struct FusedArgs {
   long long cap, max_iter;
   double tol;
   long long* stats;  // optional (SPB_FUSED_STATS=1): clocks of CTA 0 per phase, see the lap() calls
+  int slots_per_thread;  // ceil(n / threads of the grid): shared-memory slots a thread needs per vector
+  unsigned poll_sleep;   // ns between two polls of the grid barrier (0: spin)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
@@ -294,8 +296,7 @@ __device__ __forceinline__ scal2 acc_round(const AccC& a) {
 // (constant for the whole kernel, L1-resident after the first iteration), x at L2.  Gathers are issued
 // 8 per batch: a row of <= 8 entries costs one L2 round trip.
 template <typename T>
-__device__ __forceinline__ T fused_row(const FusedArgs<T>& a, int i, const T* src) {
-  const int p0 = __ldg(a.indptr + i), p1 = __ldg(a.indptr + i + 1);
+__device__ __forceinline__ T fused_row(const FusedArgs<T>& a, int p0, int p1, const T* src) {
   T acc = zero_of<T>();
   for (int k = p0; k < p1; k += 8) {
     int c[8];
@@ -315,27 +316,59 @@ __device__ __forceinline__ T fused_row(const FusedArgs<T>& a, int i, const T* sr
   return acc;
 }
 
+// the next own row's column / value lines into L1 while the current row waits for its gathers
+template <typename T>
+__device__ __forceinline__ void fused_prefetch_row(const FusedArgs<T>& a, int p0, int p1) {
+  if (p1 > p0) {
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cols + p0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.vals + p0));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(a.vals + p1 - 1));
+  }
+}
 __device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename T, typename V, bool PC, int BLOCK>
+// SV: the vectors only their owning thread touches (r, r0, p, v, t, 1/diag) live in SHARED MEMORY for the
+// whole solve -- a thread owns rows gtid + k * nth, slot k * BLOCK + tid -- so the vector-update phases
+// never wait for L2 (~1000 clocks per dependent access under this load); only what other CTAs gather
+// (y, z) and x go to global memory.  Falls back to global vectors (SV = false) when the slots do not fit.
+template <typename T, typename V, bool PC, int BLOCK, bool SV>
 __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T> a) {
   constexpr int NW = BLOCK / 32;
+  extern __shared__ __align__(16) unsigned char fused_smem[];
   __shared__ BicgState<T> S;
   __shared__ Acc<T> wsum[2][NW];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int gtid = blockIdx.x * BLOCK + tid, nth = gridDim.x * BLOCK, n = a.n;
-  const V* dinv = static_cast<const V*>(a.dinv);
+  const V* dinv_g = static_cast<const V*>(a.dinv);
   double* hist = blockIdx.x == 0 ? a.hist : nullptr;  // one writer
   unsigned long long target = 0;
   int rp = 0;  // reduction points cycle through three partial buffers (a buffer is re-written two barriers later)
   scal2 red[2];
+  // own-row vectors: shared memory (slot = k * BLOCK + tid) or global (index = row)
+  const int slots = a.slots_per_thread * BLOCK;
+  T* const sm = reinterpret_cast<T*>(fused_smem);
+  T* const r_v = SV ? sm : a.r;
+  T* const r0_v = SV ? sm + slots : a.r0;
+  T* const p_v = SV ? sm + 2 * slots : a.p;
+  T* const v_v = SV ? sm + 3 * slots : a.v;
+  T* const t_v = SV ? sm + 4 * slots : a.t;
+  const V* const d_v = SV ? reinterpret_cast<const V*>(sm + 5 * slots) : dinv_g;
+  // row extents of the own rows (shared memory: one dependent L2 round trip less per SpMV row)
+  const int2* const ext_v = reinterpret_cast<const int2*>(fused_smem + (size_t)slots * (5 * sizeof(T) + (PC ? sizeof(V) : 0)));
+  auto extent = [&](int k, int i) -> int2 {
+    if (SV) return ext_v[k * BLOCK + tid];
+    return make_int2(__ldg(a.indptr + i), __ldg(a.indptr + i + 1));
+  };
+#define SPB_OWN(k, i) (SV ? (k) * BLOCK + tid : (i))
+#define SPB_ROWS(k, i) for (int k = 0, i = gtid; i < n; ++k, i += nth)
   long long t_last = a.stats ? clock64() : 0;
-  auto lap = [&](int k) {  // diagnostics: phase clocks of CTA 0
+  long long t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  auto lap = [&](int k) {  // diagnostics: phase clocks of CTA 0 (accumulated in registers, stored at the end)
     if (a.stats && blockIdx.x == 0 && tid == 0) {
       const long long now = clock64();
-      a.stats[k] += now - t_last;
+      t_acc[k] += now - t_last;
       t_last = now;
     }
   };
@@ -349,13 +382,14 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
       target += gridDim.x;
       red_release_gpu_add(a.bar, 1ULL);
       while (ld_acquire_gpu_u64(a.bar) < target) {
+        if (a.poll_sleep) __nanosleep(a.poll_sleep);
       }
     }
     __syncthreads();
   };
   // A reduction point.  Block partial: warp shuffles, one shared-memory hop, the first warp folds the
-  // warps; after the barrier EVERY WARP of every CTA sums all CTA partials itself (fixed order, both
-  // slots interleaved) and rounds once: red[] lands in registers, identical everywhere.
+  // warps; after the barrier the FIRST WARP of every CTA sums all CTA partials itself (fixed order, both
+  // slots interleaved) and rounds once: red[] lands in the registers of thread 0, identical in every CTA.
   auto reduce = [&](Acc<T> e0, Acc<T> e1, bool two) {
     e0 = warp_sum(e0);
     if (two) e1 = warp_sum(e1);
@@ -378,15 +412,17 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     lap(5);  // block partial
     grid_sync();
     lap(6);  // barrier of a reduction point
-    Acc<T> g0 = zero_of<Acc<T>>(), g1 = zero_of<Acc<T>>();
-    for (int i = lane; i < (int)gridDim.x; i += 32) {
-      g0 = add(g0, ld_l2(pb + 2 * i));
-      if (two) g1 = add(g1, ld_l2(pb + 2 * i + 1));
+    if (wid == 0) {
+      Acc<T> g0 = zero_of<Acc<T>>(), g1 = zero_of<Acc<T>>();
+      for (int i = lane; i < (int)gridDim.x; i += 32) {
+        g0 = add(g0, ld_l2(pb + 2 * i));
+        if (two) g1 = add(g1, ld_l2(pb + 2 * i + 1));
+      }
+      g0 = warp_sum(g0);
+      if (two) g1 = warp_sum(g1);
+      red[0] = acc_round<T>(g0);
+      red[1] = acc_round<T>(g1);  // (valid in lane 0 = thread 0, the only consumer)
     }
-    g0 = warp_sum(g0);
-    if (two) g1 = warp_sum(g1);
-    red[0] = acc_round<T>(g0);
-    red[1] = acc_round<T>(g1);  // (valid in lane 0 of every warp; thread 0 is the only consumer)
     rp = rp == 2 ? 0 : rp + 1;
     lap(7);  // sum of the CTA partials
   };
@@ -394,10 +430,15 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
   auto residual = [&](int restart) {
     Acc<T> e0 = zero_of<Acc<T>>();
     const T m1 = neg(one_of<T>());
-    for (int i = gtid; i < n; i += nth) {
-      const T ri = add(fused_row(a, i, a.x), mul(a.rhs[i], m1));
-      a.r[i] = ri;
-      a.r0[i] = ri;
+    SPB_ROWS(k, i) {
+      const int2 e = extent(k, i);
+      if (SV && i + nth < n) {
+        const int2 en = extent(k + 1, i + nth);
+        fused_prefetch_row(a, en.x, en.y);
+      }
+      const T ri = add(fused_row(a, e.x, e.y, a.x), mul(a.rhs[i], m1));
+      r_v[SPB_OWN(k, i)] = ri;
+      r0_v[SPB_OWN(k, i)] = ri;
       acc_sq(e0, ri);
     }
     reduce(e0, zero_of<Acc<T>>(), false);
@@ -406,18 +447,23 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
   };
   // everything of an iteration after the S1 test; returns false when the solve ended (breakdown)
   auto iteration = [&](bool first) -> bool {
-    {  // K1
+    {  // K1: p, y = M p (y is what the other CTAs gather)
       const T c_pv = S.c_pv, beta = S.beta, one = one_of<T>();
-      for (int i = gtid; i < n; i += nth) {
+      SPB_ROWS(k, i) {
+        const int o = SPB_OWN(k, i);
         T pi;
         if (first) {
-          pi = a.r[i];
+          pi = r_v[o];
         } else {
-          pi = add(mul(a.v[i], c_pv), mul(a.p[i], beta));
-          pi = add(pi, mul(a.r[i], one));
+          pi = add(mul(v_v[o], c_pv), mul(p_v[o], beta));
+          pi = add(pi, mul(r_v[o], one));
         }
-        a.p[i] = pi;
-        if (PC) a.y[i] = mul_diag(pi, dinv[i]);
+        p_v[o] = pi;
+        a.y[i] = PC ? mul_diag(pi, d_v[o]) : pi;
+      }
+      if (SV && gtid < n) {  // first row of the SpMV that follows the barrier
+        const int2 e0 = extent(0, gtid);
+        fused_prefetch_row(a, e0.x, e0.y);
       }
     }
     lap(0);  // K1
@@ -425,10 +471,16 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     lap(8);  // plain barrier
     {  // v = A y, <r0, v>
       Acc<T> e0 = zero_of<Acc<T>>();
-      for (int i = gtid; i < n; i += nth) {
-        const T vi = fused_row(a, i, a.y);
-        a.v[i] = vi;
-        acc_prod(e0, conj_of(a.r0[i]), vi);
+      SPB_ROWS(k, i) {
+        const int o = SPB_OWN(k, i);
+        const int2 e = extent(k, i);
+        if (SV && i + nth < n) {
+          const int2 en = extent(k + 1, i + nth);
+          fused_prefetch_row(a, en.x, en.y);
+        }
+        const T vi = fused_row(a, e.x, e.y, a.y);
+        v_v[o] = vi;
+        acc_prod(e0, conj_of(r0_v[o]), vi);
       }
       lap(1);  // SpMV 1
       reduce(e0, zero_of<Acc<T>>(), false);
@@ -437,12 +489,17 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     __syncthreads();
     lap(9);  // scalar step
     if (S.h.status != DS_RUNNING) return false;
-    {  // K2
+    {  // K2: r -= alpha v, z = M r
       const T nalpha = S.nalpha;
-      for (int i = gtid; i < n; i += nth) {
-        const T ri = add(a.r[i], mul(a.v[i], nalpha));
-        a.r[i] = ri;
-        if (PC) a.z[i] = mul_diag(ri, dinv[i]);
+      SPB_ROWS(k, i) {
+        const int o = SPB_OWN(k, i);
+        const T ri = add(r_v[o], mul(v_v[o], nalpha));
+        r_v[o] = ri;
+        a.z[i] = PC ? mul_diag(ri, d_v[o]) : ri;
+      }
+      if (SV && gtid < n) {
+        const int2 e0 = extent(0, gtid);
+        fused_prefetch_row(a, e0.x, e0.y);
       }
     }
     lap(2);  // K2
@@ -450,12 +507,18 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     lap(8);
     {  // t = A z, <t,t>, <t,r>
       Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
-      for (int i = gtid; i < n; i += nth) {
-        const T ti = fused_row(a, i, a.z);
-        a.t[i] = ti;
+      SPB_ROWS(k, i) {
+        const int o = SPB_OWN(k, i);
+        const int2 e = extent(k, i);
+        if (SV && i + nth < n) {
+          const int2 en = extent(k + 1, i + nth);
+          fused_prefetch_row(a, en.x, en.y);
+        }
+        const T ti = fused_row(a, e.x, e.y, a.z);
+        t_v[o] = ti;
         const T cy = conj_of(ti);
         acc_prod(e0, cy, ti);
-        acc_prod(e1, cy, a.r[i]);
+        acc_prod(e1, cy, r_v[o]);
       }
       lap(3);  // SpMV 2
       reduce(e0, e1, true);
@@ -463,18 +526,22 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     if (tid == 0) bicg_s3_body(&S, red);
     __syncthreads();
     lap(9);
-    {  // K3 + the partials of the next iteration's test
+    {  // K3 + the partials of the next iteration's test.  y_i, z_i of the own rows are recomputed from p and r
+       // (the same single operation on the same operands: the same bits) instead of re-read from global.
       Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
       const T nalpha = S.nalpha, nw = S.nw;
-      for (int i = gtid; i < n; i += nth) {
-        const T zi = a.z[i];
-        T xi = add(a.x[i], mul(a.y[i], nalpha));
+      SPB_ROWS(k, i) {
+        const int o = SPB_OWN(k, i);
+        const T pi = p_v[o], si = r_v[o];
+        const T yi = PC ? mul_diag(pi, d_v[o]) : pi;
+        const T zi = PC ? mul_diag(si, d_v[o]) : si;
+        T xi = add(a.x[i], mul(yi, nalpha));
         xi = add(xi, mul(zi, nw));
         a.x[i] = xi;
-        const T ri = add(a.r[i], mul(a.t[i], nw));
-        a.r[i] = ri;
+        const T ri = add(si, mul(t_v[o], nw));
+        r_v[o] = ri;
         acc_sq(e0, ri);
-        acc_prod(e1, conj_of(a.r0[i]), ri);
+        acc_prod(e1, conj_of(r0_v[o]), ri);
       }
       lap(4);  // K3
       reduce(e0, e1, true);
@@ -486,6 +553,14 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     memset(&S, 0, sizeof(S));
     S.h.status = DS_RUNNING;
     S.tol = (real_t<T>)a.tol;
+  }
+  if (SV) {  // row extents and 1 / diag of the own rows
+    int2* ew = reinterpret_cast<int2*>(fused_smem + (size_t)slots * (5 * sizeof(T) + (PC ? sizeof(V) : 0)));
+    V* dw = reinterpret_cast<V*>(sm + 5 * slots);
+    SPB_ROWS(k, i) {
+      ew[k * BLOCK + tid] = make_int2(__ldg(a.indptr + i), __ldg(a.indptr + i + 1));
+      if (PC) dw[k * BLOCK + tid] = dinv_g[i];
+    }
   }
   __syncthreads();
   {  // ||b||  (:225-231)
@@ -510,7 +585,13 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
       }
     }
   }
-  if (blockIdx.x == 0 && tid == 0) *a.st = S;
+  if (blockIdx.x == 0 && tid == 0) {
+    *a.st = S;
+    if (a.stats)
+      for (int k = 0; k < 10; ++k) a.stats[k] = t_acc[k];
+  }
+#undef SPB_OWN
+#undef SPB_ROWS
 }
 
 // ---------------------------------------------------------------- host driver
@@ -596,8 +677,10 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
 
   if (fused_eligible(Am, pcm)) {
     // the whole solve in one cooperative kernel (see bicg_fused_kernel)
-    FusedArgs<T> fa{bufptr<int>(Am->indptr), bufptr<int>(Am->cols), bufptr<T>(Am->vals), (int)n, rhs, x, r, r0, p, y, v, t, z,
-                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol, nullptr};
+    // (y and z are always separate buffers here: they are what the other CTAs gather)
+    FusedArgs<T> fa{bufptr<int>(Am->indptr), bufptr<int>(Am->cols), bufptr<T>(Am->vals), (int)n, rhs, x, r, r0, p, w0 + 3 * n, v, t, w0 + 6 * n,
+                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol, nullptr, 0, 0};
+    if (const char* ps = getenv("SPB_FUSED_POLL_NS")) fa.poll_sleep = (unsigned)atoi(ps);
     const bool want_stats = getenv("SPB_FUSED_STATS") != nullptr;
     if (want_stats) {
       fused_stats.ensure(sizeof(long long) * 16);
@@ -802,13 +885,17 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
   FusedArgs<T> fa = fa0;
   const char* be = getenv("SPB_FUSED_BLOCK");
   const int block = be && *be ? atoi(be) : 512;
-  auto run = [&](auto kern, int BLOCK) {
-    int bps = 0;
-    SPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, BLOCK, 0));
-    if (bps < 1) SPB_FAIL(SPB_CUDA_ERROR, "single-kernel BiCGStab does not fit on an SM");
-    const char* ge = getenv("SPB_FUSED_CTAS_PER_SM");
-    const int per_sm = std::max(1, std::min(bps, ge && *ge ? atoi(ge) : 1));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count * per_sm, ceil_div(n, BLOCK)));
+  const char* se = getenv("SPB_FUSED_SMEM");
+  const bool allow_smem = !(se && *se == '0');
+  int smem_cap = 0;
+  SPB_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  auto run = [&](auto kern_sv, auto kern_gl, int BLOCK) {
+    // one CTA per SM (the shared-memory variant needs most of an SM's shared memory anyway)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count, ceil_div(n, BLOCK)));
+    const int spt = (int)ceil_div(n, (int64_t)grid * BLOCK);
+    const size_t smem = ((size_t)5 * sizeof(T) + (PC ? sizeof(V) : 0) + sizeof(int2)) * (size_t)spt * BLOCK + 16;
+    const bool sv = allow_smem && smem + 4096 <= (size_t)smem_cap;
+    fa.slots_per_thread = spt;
     fused_parts.ensure(sizeof(Acc<T>) * 6 * (size_t)grid);
     fused_bar.ensure(sizeof(unsigned long long) * 2);
     fa.parts = bufptr<Acc<T>>(fused_parts);
@@ -816,14 +903,19 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
     SPB_CUDA(cudaMemsetAsync(fused_bar.p, 0, sizeof(unsigned long long) * 2, c->stream));
     LaunchScope ls(c, FAM_VEC);
     void* args[] = {(void*)&fa};
-    SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(BLOCK), args, 0, c->stream));
+    if (sv) {
+      SPB_CUDA(cudaFuncSetAttribute(kern_sv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern_sv, dim3(grid), dim3(BLOCK), args, smem, c->stream));
+    } else {
+      SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern_gl, dim3(grid), dim3(BLOCK), args, 0, c->stream));
+    }
   };
   if (block >= 1024)
-    run(bicg_fused_kernel<T, V, PC, 1024>, 1024);
+    run(bicg_fused_kernel<T, V, PC, 1024, true>, bicg_fused_kernel<T, V, PC, 1024, false>, 1024);
   else if (block >= 512)
-    run(bicg_fused_kernel<T, V, PC, 512>, 512);
+    run(bicg_fused_kernel<T, V, PC, 512, true>, bicg_fused_kernel<T, V, PC, 512, false>, 512);
   else
-    run(bicg_fused_kernel<T, V, PC, 256>, 256);
+    run(bicg_fused_kernel<T, V, PC, 256, true>, bicg_fused_kernel<T, V, PC, 256, false>, 256);
 }
 
 spb_solver* make_bicgstab(spb_op* A, int64_t size) {

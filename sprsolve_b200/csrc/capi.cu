@@ -547,7 +547,9 @@ int spb_diag_precond_from_csr(spb_op* m, spb_op** out) {
   SPB_CATCH
 }
 
-int spb_gs_precond_create(spb_op* m, int mode, spb_op** out) {
+int spb_gs_precond_create(spb_op* m, int mode, spb_op** out) { return spb_gs_precond_create_relaxed(m, mode, 1.0, out); }
+
+int spb_gs_precond_create_relaxed(spb_op* m, int mode, double omega, spb_op** out) {
   SPB_TRY
   SPB_REQUIRE(m && out, "null argument");
   *out = nullptr;
@@ -559,7 +561,7 @@ int spb_gs_precond_create(spb_op* m, int mode, spb_op** out) {
   spb_op* op = nullptr;
   int64_t bad = -1;
   SPB_WITH_DTYPE(m->dtype, {
-    auto* g = gs_create(static_cast<CsrMat<T>*>(m), mode);
+    auto* g = gs_create(static_cast<CsrMat<T>*>(m), mode, omega);
     bad = g->bad_row;
     op = g;
   });
@@ -773,13 +775,13 @@ int spb_vec_axpby(spb_ctx* c, int dtype, int64_t n, const double a[2], const voi
 }
 
 // ---------------------------------------------------------------- solvers
-static int make_solver(spb_op* A, int64_t size, int which, spb_solver** out) {
+static int make_solver(spb_op* A, int64_t size, int which, spb_solver** out, double omega = 1.0) {
   SPB_TRY
   SPB_REQUIRE(A && out && size >= 0, "bad argument");
   *out = nullptr;
   use_device(A->ctx);
   if (which == 3)
-    *out = make_gauss_seidel(A);
+    *out = make_gauss_seidel(A, omega);
   else {
     SPB_REQUIRE(A->kind == OP_CSR, "solver operator must be a CSR matrix");
     *out = which == 0 ? make_bicgstab(A, size) : make_minres(A, size, which == 2);
@@ -792,6 +794,9 @@ int spb_bicgstab_create(spb_op* A, int64_t size, spb_solver** out) { return make
 int spb_minres_create(spb_op* A, int64_t size, spb_solver** out) { return make_solver(A, size, 1, out); }
 int spb_csminres_create(spb_op* A, int64_t size, spb_solver** out) { return make_solver(A, size, 2, out); }
 int spb_gauss_seidel_create(spb_op* A, spb_solver** out) { return make_solver(A, A ? A->n_local : 0, 3, out); }
+int spb_gauss_seidel_create_relaxed(spb_op* A, double omega, spb_solver** out) {
+  return make_solver(A, A ? A->n_local : 0, 3, out, omega);
+}
 
 int spb_solver_solve_dev(spb_solver* s, spb_op* precond, const void* d_rhs, void* d_x, int64_t max_iter,
                          double tol, int64_t* iters, double* resid, double* hist, int64_t hist_cap,

@@ -51,13 +51,13 @@ template <typename T>
 struct GaussSeidelSolver : spb_solver {
   GsOp<T>* gs = nullptr;
   DevBuf res, xalt, partials, red, state, hist_d;
-  explicit GaussSeidelSolver(spb_op* A_) {
+  explicit GaussSeidelSolver(spb_op* A_, double omega) {
     A = A_;
     ctx = A_->ctx;
     kind = 3;
     dtype = ScalarTraits<T>::dtype;
     size = A_->n_local;
-    gs = gs_create<T>(static_cast<CsrMat<T>*>(A_), SPB_GS_FORWARD);
+    gs = gs_create<T>(static_cast<CsrMat<T>*>(A_), SPB_GS_FORWARD, omega);
     const size_t n1 = (size_t)std::max<int64_t>(size, 1);
     res.alloc(sizeof(T) * n1);   // workspace[0..n]   (src/gauss_seidel.rs:29)
     xalt.alloc(sizeof(T) * n1);
@@ -174,16 +174,16 @@ int GaussSeidelSolver<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int
   return rc;
 }
 
-spb_solver* make_gauss_seidel(spb_op* A) {
+spb_solver* make_gauss_seidel(spb_op* A, double omega) {
   if (A->kind != OP_CSR) {
     set_last_error("Not in CSR format");  // src/gauss_seidel.rs:22-26
     throw SpbError{SPB_INCOMPATIBLE_FORMAT};
   }
   switch (A->dtype) {
-    case SPB_F64: return new GaussSeidelSolver<double>(A);
-    case SPB_C128: return new GaussSeidelSolver<cplx>(A);
-    case SPB_F32: return new GaussSeidelSolver<float>(A);
-    default: return new GaussSeidelSolver<cplxf>(A);
+    case SPB_F64: return new GaussSeidelSolver<double>(A, omega);
+    case SPB_C128: return new GaussSeidelSolver<cplx>(A, omega);
+    case SPB_F32: return new GaussSeidelSolver<float>(A, omega);
+    default: return new GaussSeidelSolver<cplxf>(A, omega);
   }
 }
 

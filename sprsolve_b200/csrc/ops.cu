@@ -186,6 +186,11 @@ struct GsArgs {
   unsigned long long* counter;
   const int* gate;
   int gate_value;
+  // relaxed sweep (SOR / SSOR(omega); not in the reference): x_i <- (1 - omega) xold_i + omega g_i, computed as
+  // mul_real(xold_i, 1 - omega) + mul_real(g_i, omega); xold null = a sweep from zero.  relaxed == 0: plain sweep.
+  int relaxed;
+  real_t<T> omega;
+  const T* xold;
 };
 
 template <typename T, typename IP>
@@ -208,7 +213,12 @@ __global__ void __launch_bounds__(256) gs_sweep_kernel(const GsArgs<T, IP> a) {
           if (a.hi_src) sigma = add(sigma, mul(a.vals[k], ld_cg(a.hi_src + col)));
         }
       }
-      a.out[row] = divi(sub(a.rhs[row], sigma), a.diag[row]);  // :123
+      T g = divi(sub(a.rhs[row], sigma), a.diag[row]);  // :123
+      if (a.relaxed) {
+        const T xo = a.xold ? ld_cg(a.xold + row) : zero_of<T>();
+        g = add(mul_real(xo, (real_t<T>)1 - a.omega), mul_real(g, a.omega));
+      }
+      a.out[row] = g;
     }
     if (lvl + 1 < a.nlevels) grid_barrier(a.counter, target);
   }
@@ -247,8 +257,9 @@ static void build_levels(Ctx* c, int64_t n, const std::vector<int64_t>& ip, cons
 }
 
 template <typename T>
-GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
+GsOp<T>* gs_create(CsrMat<T>* A, int mode, double omega) {
   Ctx* c = A->ctx;
+  if (!(omega > 0.0 && omega < 2.0)) SPB_FAIL(SPB_INVALID_ARG, "relaxation factor must lie in (0, 2)");
   if (c->world() > 1)
     SPB_FAIL(SPB_INVALID_ARG, "Gauss-Seidel in natural order does not partition across GPUs (replicas only)");
   if (mode != SPB_GS_FORWARD && mode != SPB_GS_SYMMETRIC) SPB_FAIL(SPB_INVALID_ARG, "bad gs mode");
@@ -260,6 +271,8 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
     op->n_global = op->n_local = A->n_local;
     op->A = A;
     op->mode = mode;
+    op->omega = omega;
+    const bool relaxed = (real_t<T>)omega != (real_t<T>)1;
     const int64_t n = A->n_local;
     op->diag.alloc(sizeof(T) * (size_t)std::max<int64_t>(n, 1));
     op->tmp.alloc(sizeof(T) * (size_t)std::max<int64_t>(n, 1));
@@ -291,7 +304,8 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
       SPB_CUDA(cudaStreamSynchronize(c->stream));
       int bwd_status = SPB_OK;
       std::thread bwd_thread;
-      if (mode == SPB_GS_SYMMETRIC)
+      // (the relaxed sweeps run on the level-scheduled kernel: no wavefront schedules)
+      if (mode == SPB_GS_SYMMETRIC && !relaxed)
         bwd_thread = std::thread([&]() {
           try {
             SPB_CUDA(cudaSetDevice(c->device));
@@ -304,7 +318,7 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode) {
         });
       int fwd_status = SPB_OK;
       try {
-        wave_build<T>(A, ip, cols, vals, false, op->wfwd);
+        if (!relaxed) wave_build<T>(A, ip, cols, vals, false, op->wfwd);
       } catch (const SpbError& e) {
         fwd_status = e.status;
       } catch (...) {  // e.g. std::bad_alloc from the host vectors: never unwind past a joinable thread
@@ -358,13 +372,14 @@ static void ensure_levels(GsOp<T>* M) {
 }
 
 template <typename T, typename IP>
-static void launch_sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, const T* hi, T* out) {
+static void launch_sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, const T* hi, T* out, const T* xold) {
   Ctx* c = M->ctx;
   CsrMat<T>* A = M->A;
   if (A->n_local == 0) return;
   GsArgs<T, IP> a{bufptr<IP>(A->indptr), bufptr<int>(A->cols), bufptr<T>(A->vals), bufptr<T>(M->diag),
                   bufptr<int>(ls.level_ptr), bufptr<int>(ls.rows), (int)ls.nlevels, rhs, lo, hi, out,
-                  bufptr<unsigned long long>(M->barrier), c->gate, c->gate_value};
+                  bufptr<unsigned long long>(M->barrier), c->gate, c->gate_value,
+                  (real_t<T>)M->omega != (real_t<T>)1 ? 1 : 0, (real_t<T>)M->omega, xold};
   int bps = 0;  // per call (per device): a process may hold contexts on several GPUs
   auto kern = gs_sweep_kernel<T, IP>;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, 256, 0);
@@ -380,8 +395,9 @@ static void launch_sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T
   SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(256), args, 0, c->stream));
 }
 
+// xold: the values the relaxed update mixes with (null: zero); ignored by the plain sweep
 template <typename T>
-static void sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, const T* hi, T* out) {
+static void sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, const T* hi, T* out, const T* xold = nullptr) {
   // fast path: block-wavefront sweep (the produced side must be the vector being written; rhs and
   // the other triangle are consumed by its pre-pass, so out may alias them)
   const bool fwd = &ls == &M->fwd;
@@ -393,9 +409,9 @@ static void sweep(GsOp<T>* M, const LevelSched& ls, const T* rhs, const T* lo, c
   }
   ensure_levels(M);
   if (M->A->ip64)
-    launch_sweep<T, int64_t>(M, ls, rhs, lo, hi, out);
+    launch_sweep<T, int64_t>(M, ls, rhs, lo, hi, out, xold);
   else
-    launch_sweep<T, int32_t>(M, ls, rhs, lo, hi, out);
+    launch_sweep<T, int32_t>(M, ls, rhs, lo, hi, out, xold);
 }
 
 template <typename T>
@@ -404,14 +420,14 @@ void gs_apply(GsOp<T>* M, const T* in, T* out) {
     sweep<T>(M, M->fwd, in, out, nullptr, out);
   } else {
     T* tmp = bufptr<T>(M->tmp);
-    sweep<T>(M, M->fwd, in, tmp, nullptr, tmp);  // forward sweep from zero
-    sweep<T>(M, M->bwd, in, tmp, out, out);      // rows n-1..0: lower cols = forward values
+    sweep<T>(M, M->fwd, in, tmp, nullptr, tmp);       // forward sweep from zero
+    sweep<T>(M, M->bwd, in, tmp, out, out, tmp);      // rows n-1..0: lower cols = forward values (relaxed: mixed with them)
   }
 }
 
 template <typename T>
 void gs_solver_sweep(GsOp<T>* M, const T* rhs, const T* x_old, T* x_new) {
-  sweep<T>(M, M->fwd, rhs, x_new, x_old, x_new);
+  sweep<T>(M, M->fwd, rhs, x_new, x_old, x_new, x_old);
 }
 
 template <typename T>
@@ -434,7 +450,7 @@ void op_apply(spb_op* op, const T* in, T* out) {
 #define SPB_INST(T)                                                              \
   template DiagOp<T>* diag_from_host<T>(Ctx*, int, const void*, int64_t);        \
   template DiagOp<T>* diag_from_csr<T>(CsrMat<T>*);                              \
-  template GsOp<T>* gs_create<T>(CsrMat<T>*, int);                               \
+  template GsOp<T>* gs_create<T>(CsrMat<T>*, int, double);                       \
   template void csr_diagonal<T>(CsrMat<T>*, T*);                                 \
   template void diag_apply<T>(DiagOp<T>*, const T*, T*);                         \
   template void gs_apply<T>(GsOp<T>*, const T*, T*);                             \

@@ -64,6 +64,7 @@ template <typename T>
 struct GsOp : spb_op {
   CsrMat<T>* A = nullptr;
   int mode = SPB_GS_FORWARD;
+  double omega = 1.0;   // relaxation factor: != 1 selects the relaxed sweep (SOR / SSOR(omega)), level-scheduled kernel
   DevBuf diag;          // T [n] cached diagonal (src/gauss_seidel.rs:81)
   LevelSched fwd, bwd;  // lower / upper pattern, global levels: the fallback sweep (built on first use)
   bool levels_ready = false;
@@ -79,7 +80,7 @@ DiagOp<T>* diag_from_host(Ctx* ctx, int diag_dtype, const void* diag, int64_t n)
 template <typename T>
 DiagOp<T>* diag_from_csr(CsrMat<T>* A);
 template <typename T>
-GsOp<T>* gs_create(CsrMat<T>* A, int mode);
+GsOp<T>* gs_create(CsrMat<T>* A, int mode, double omega = 1.0);
 template <typename T>
 void csr_diagonal(CsrMat<T>* A, T* d_diag);  // device out, 0 where absent
 

@@ -65,7 +65,7 @@ inline PcMode pc_mode_of(spb_op* M) {
 
 spb_solver* make_bicgstab(spb_op* A, int64_t size);
 spb_solver* make_minres(spb_op* A, int64_t size, bool cs);
-spb_solver* make_gauss_seidel(spb_op* A);
+spb_solver* make_gauss_seidel(spb_op* A, double omega = 1.0);
 
 // Lagged status polling through pinned memory.
 struct Poller {

@@ -22,17 +22,17 @@ for g in (100, 256, 512):
     x = torch.zeros(g * g, dtype=torch.float64, device=dev)
     M = sp.DiagPrecond.from_matrix(A)
     S = sp.BiCGStab(A, g * g)
-    for block in (256, 512, 1024):
-        for per_sm in (1, 2):
+    for block in [int(b) for b in os.environ.get("TUNE_BLOCKS", "256,512,1024").split(",")]:
+        for smem in ("1", "0"):
             os.environ["SPB_FUSED"] = "1"
             os.environ["SPB_FUSED_BLOCK"] = str(block)
-            os.environ["SPB_FUSED_CTAS_PER_SM"] = str(per_sm)
+            os.environ["SPB_FUSED_SMEM"] = smem
             ts = []
-            for _ in range(4):
+            for _ in range(3):
                 x.zero_()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 it, res = S.solve_dev(rhs.data_ptr(), x.data_ptr(), 10000, 1e-8, precond=M)
                 ts.append(time.perf_counter() - t0)
             t = min(ts[1:])
-            print(f"grid {g:4d}  block {block:5d} x {per_sm}/SM  its {it:5d}  solve {1e3 * t:8.3f} ms  {1e6 * t / it:7.2f} us/iter", flush=True)
+            print(f"grid {g:4d}  block {block:5d}  smem-vectors {smem}  its {it:5d}  solve {1e3 * t:8.3f} ms  {1e6 * t / it:7.2f} us/iter", flush=True)
