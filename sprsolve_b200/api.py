@@ -166,12 +166,24 @@ class Context:
 
     # multi-GPU: one process per GPU, id created on rank 0 and broadcast by the caller
     @staticmethod
+    def _prefer_torch_nccl():
+        """The library resolves NCCL at run time (dlopen by soname).  When PyTorch is installed, load ITS copy
+        first: two NCCL builds with the same soname cannot coexist in one process, and a torch imported
+        after the system copy was mapped fails to resolve the newer symbols it was built against."""
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
+
+    @staticmethod
     def comm_unique_id() -> bytes:
+        Context._prefer_torch_nccl()
         buf = C.create_string_buffer(128)
         _check(F.lib().spb_comm_unique_id(buf))
         return buf.raw
 
     def comm_init(self, world: int, rank: int, unique_id: bytes):
+        Context._prefer_torch_nccl()
         buf = C.create_string_buffer(bytes(unique_id), 128)
         _check(F.lib().spb_comm_init(self._h, world, rank, buf))
 
@@ -369,7 +381,10 @@ class GpuCsrMat(MatVecMul):
         v = (C.c_int64 * 8)()
         _check(F.lib().spb_csr_plan_info(self._h, v))
         keys = ["dictionary", "patterns", "dict_width", "consumer_threads", "stages", "tile_nnz", "ctas_per_sm", "stream_bytes"]
-        return {k: int(v[i]) for i, k in enumerate(keys)}
+        d = {k: int(v[i]) for i, k in enumerate(keys)}
+        d["x_window"] = (d["dictionary"] >> 1) & 1  # x segments staged in shared memory by bulk copies
+        d["dictionary"] &= 1
+        return d
 
     def download(self):
         """(indptr int64, indices int32 global, data) of the local rows."""

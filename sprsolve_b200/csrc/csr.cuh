@@ -15,6 +15,8 @@ enum SpmvEpiMode {
   EPI_TT_TR = 2    // slot0 = sum conj(y_i) * y_i, slot1 = sum conj(y_i) * w_i   (<t,t>, <t,r>)
 };
 
+static const int kMaxXwinSegs = 32;
+
 struct HaloPeer {
   int rank;
   int64_t send_off, send_cnt;  // into sendbuf / send_idx
@@ -61,6 +63,20 @@ struct CsrMat : spb_op {
   int64_t dict_u = 0;    // number of distinct row patterns
   DevBuf dict_off;       // int32 [dict_u * dict_w]: col - row of the pattern's entries
   DevBuf pid;            // uint16 [n_local]: pattern id of every row
+  // --- x window (spmv.cu): the distinct column offsets of a stencil-like matrix form a few runs of
+  //     consecutive values; per tile the x entries of every run are ONE contiguous segment, staged in
+  //     shared memory with a bulk copy, and the gathers become shared-memory reads
+  bool xwin_on = false;
+  bool xwin_want = false;            // SPB_SPMV_XWIN=1, or chosen by autotune()
+  std::vector<int> dict_off_host, dict_len_host;  // host copies of the dictionary (analysis of the runs)
+  int xwin_nseg = 0;                 // runs of consecutive offsets
+  int xwin_rows = 0;                 // most rows of a tile the window is laid out for
+  int xwin_elems = 0;                // shared-memory elements of one window
+  int xwin_gmin[kMaxXwinSegs] = {};  // first offset of the run
+  int xwin_pad[kMaxXwinSegs] = {};   // elements the copy starts before it (16-byte alignment)
+  int xwin_extra[kMaxXwinSegs] = {}; // pad + (last - first offset): copy length = extra + rows, rounded up
+  int xwin_start[kMaxXwinSegs] = {}; // first shared-memory element of the segment
+  DevBuf dict_soff;                  // int32 [dict_u * dict_w]: window element of (local row 0, entry)
 
   // --- row-block partition (multi-GPU) ------------------------------------------------------
   int64_t n_halo = 0;
@@ -81,6 +97,8 @@ struct CsrMat : spb_op {
   DevBuf stage_in, stage_out;
 
   void analyze();
+  void choose_format();
+  void static_plan(int& consumer_threads, int& stages);
   void build_plan(int consumer_threads, int stages);
   void autotune();
   // y = A x (x, y device pointers to LOCAL vectors).  conj_in: multiply by conj(x) (CSMinRes,

@@ -22,6 +22,11 @@
 // Algorithmic bytes per launch: nnz*(sizeof(T)+4) + (n+1)*sizeof(indptr) + 2*n*sizeof(T).
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cmath>
+#include <utility>
+#include <vector>
+
 #include "csr.cuh"
 #include "dist.cuh"
 #include "reduce.cuh"
@@ -86,6 +91,12 @@ struct SpmvArgs {
   const int* doff;
   int dict_w;
   int* err;  // Ctx::dev_err: set when a neighbour's halo flag never arrived
+  // x window (DICT kernels, xw_nseg > 0): per tile the x entries of every run of consecutive column
+  // offsets are one contiguous segment; the producer stages the segments in shared memory with bulk
+  // copies and row r reads entry k at window element soff[pid[r] * dict_w + k] + (r - r0)
+  const int* soff;
+  int xw_nseg, xw_rows, xw_elems;
+  int xw_gmin[kMaxXwinSegs], xw_pad[kMaxXwinSegs], xw_extra[kMaxXwinSegs], xw_start[kMaxXwinSegs];
 };
 
 // x entry for local column id c.  Single GPU (HALO = false): every column is owned.  Partitioned
@@ -117,6 +128,8 @@ struct TileMeta {
   int total;      // staged non-zeros counted from the 4-aligned base; -1 => long-row tile
   int ip_off;     // index of indptr[r0] inside the staged indptr slice; -1 => slice not staged
   long long s4;   // 4-aligned first non-zero
+  int win;        // the stage carries the x window of this tile
+  int pad;
 };
 
 __host__ __device__ inline int align16i(int v) { return (v + 15) & ~15; }
@@ -159,7 +172,8 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   const int VAL_BYTES = align16i((a.tile + 4) * (int)sizeof(T));
   const int COL_BYTES = DICT ? 0 : align16i((a.tile + 4) * 4);  // DICT: the column stream is not read at all
   const int IP_BYTES = align16i((a.rcap + 8) * (int)sizeof(IP));
-  const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES;  // vals | cols | indptr slice
+  const int XW_BYTES = DICT ? align16i(a.xw_elems * (int)sizeof(T)) : 0;
+  const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES;  // vals | cols | indptr slice | x window
   const int STAGES = a.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
   uint64_t* empty = full + kMaxStages;
@@ -194,6 +208,8 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
     if (tid == CT) {
       constexpr int IPV = 16 / (int)sizeof(IP);  // indptr entries per 16 bytes
       const uint64_t pol_stream = l2_policy_evict_first();
+      const uint64_t pol_keep = l2_policy_evict_last();
+      constexpr int XA = 16 / (int)sizeof(T) > 0 ? 16 / (int)sizeof(T) : 1;  // elements per 16 bytes
       int s = 0;
       uint32_t ph = 0;
       bool halo_ready = !(HALO && a.hhead);
@@ -226,9 +242,25 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           const int nip = ((r1 + 1 - ra) + IPV - 1) & ~(IPV - 1);
           const bool ip_ok = nip <= a.rcap + 8 - IPV;
           m.ip_off = ip_ok ? (r0 - ra) : -1;
-          meta[s] = m;
           const uint32_t groups = (uint32_t)((m.total + 3) >> 2);
-          const uint32_t bytes = groups * ((DICT ? 0u : 16u) + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u);
+          // x window: every segment must lie inside the owned part of x (tiles at the ends of the row
+          // range and tiles with halo columns gather from global memory instead)
+          const int rows = r1 - r0;
+          uint32_t xw_bytes = 0;
+          bool win = DICT && a.xw_nseg > 0 && groups > 0 && rows <= a.xw_rows && (r0 & (XA - 1)) == 0;
+          if (win) {
+            for (int g = 0; g < a.xw_nseg; ++g) {
+              const long long s0 = (long long)r0 + a.xw_gmin[g] - a.xw_pad[g];
+              const int len = (a.xw_extra[g] + rows + XA - 1) & ~(XA - 1);
+              if (s0 < 0 || s0 + len > (long long)a.n_local) win = false;
+              xw_bytes += (uint32_t)len * (uint32_t)sizeof(T);
+            }
+          }
+          m.win = win ? 1 : 0;
+          m.pad = 0;
+          meta[s] = m;
+          const uint32_t bytes = groups * ((DICT ? 0u : 16u) + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u) +
+                                 (win ? xw_bytes : 0u);
           if (bytes) {
             mbar_arrive_expect_tx(&full[s], bytes);
             if (groups) {
@@ -236,12 +268,22 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               if (!DICT) bulk_g2s(stage + VAL_BYTES, a.cols + s4, groups * 16u, &full[s], pol_stream);
             }
             if (ip_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES, a.indptr + ra, (uint32_t)nip * (uint32_t)sizeof(IP), &full[s], pol_stream);
+            if (win) {
+              unsigned char* xw = stage + VAL_BYTES + COL_BYTES + IP_BYTES;
+              for (int g = 0; g < a.xw_nseg; ++g) {
+                const long long s0 = (long long)r0 + a.xw_gmin[g] - a.xw_pad[g];
+                const int len = (a.xw_extra[g] + rows + XA - 1) & ~(XA - 1);
+                bulk_g2s(xw + (size_t)a.xw_start[g] * sizeof(T), a.x + s0, (uint32_t)len * (uint32_t)sizeof(T), &full[s], pol_keep);
+              }
+            }
           } else {
             mbar_arrive(&full[s]);
           }
         } else {
           m.total = -1;  // long-row tile: consumers read it from global memory
           m.ip_off = -1;
+          m.win = 0;
+          m.pad = 0;
           meta[s] = m;
           mbar_arrive(&full[s]);
         }
@@ -263,7 +305,39 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
       const T* s_val = reinterpret_cast<const T*>(stage);
       const int* s_col = reinterpret_cast<const int*>(stage + VAL_BYTES);
       const IP* s_ip = reinterpret_cast<const IP*>(stage + VAL_BYTES + COL_BYTES);
-      if (m.total >= 0) {
+      if (DICT && m.total >= 0 && m.win) {
+        // x window: every operand of the tile is in shared memory -- values from the stream, x from the
+        // staged segments; the same sequential fold in CSR order, no global load on the critical path
+        const T* s_xw = reinterpret_cast<const T*>(stage + VAL_BYTES + COL_BYTES + IP_BYTES);
+        for (int r = m.r0 + tid; r < m.r1; r += CT) {
+          int p0, p1;
+          row_range(a, m, s_ip, r, p0, p1);
+          T acc = zero_of<T>();
+          const int lr = r - m.r0;
+          const int4* dp = reinterpret_cast<const int4*>(a.soff + (int)a.pid[r] * a.dict_w);
+          int k = p0;
+          for (; k + 8 <= p1; k += 8) {
+            const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+            dp += 2;
+            T xv[8];
+            xv[0] = s_xw[lr + q0.x]; xv[1] = s_xw[lr + q0.y]; xv[2] = s_xw[lr + q0.z]; xv[3] = s_xw[lr + q0.w];
+            xv[4] = s_xw[lr + q1.x]; xv[5] = s_xw[lr + q1.y]; xv[6] = s_xw[lr + q1.z]; xv[7] = s_xw[lr + q1.w];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = add(acc, mul(CONJ_IN ? conj_of(xv[j]) : xv[j], s_val[k + j]));
+          }
+          if (k < p1) {
+            const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
+            T xv[8];
+            xv[0] = s_xw[lr + q0.x]; xv[1] = s_xw[lr + q0.y]; xv[2] = s_xw[lr + q0.z]; xv[3] = s_xw[lr + q0.w];
+            xv[4] = s_xw[lr + q1.x]; xv[5] = s_xw[lr + q1.y]; xv[6] = s_xw[lr + q1.z]; xv[7] = s_xw[lr + q1.w];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (k + j < p1) acc = add(acc, mul(CONJ_IN ? conj_of(xv[j]) : xv[j], s_val[k + j]));
+          }
+          a.y[r] = acc;
+          epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+        }
+      } else if (m.total >= 0) {
         // one thread per row: x gathers go to registers (ld.global.nc through L1, L2 evict_last),
         // 8 per batch, then the sequential fold in CSR order (src/mat.rs:100-105).  Full batches
         // carry no predicates; only the last (partial) batch of a row is clamped / predicated.
@@ -361,9 +435,11 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
 }
 
 // ---------------------------------------------------------------- analysis kernels
+// align: tile boundaries are rounded down to a multiple of `align` rows (x window: bulk copies of x start
+// at 16-byte boundaries)
 template <typename IP>
 __global__ void tile_rows_kernel(const IP* indptr, int64_t n, int64_t span, int64_t ntiles,
-                                 int* tile_row) {
+                                 int* tile_row, int align) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t > ntiles) return;
   if (t == ntiles) {
@@ -380,7 +456,7 @@ __global__ void tile_rows_kernel(const IP* indptr, int64_t n, int64_t span, int6
     else
       hi = mid;
   }
-  tile_row[t] = (int)lo;
+  tile_row[t] = (int)(lo & ~(int64_t)(align - 1));
 }
 
 template <typename IP>
@@ -459,13 +535,22 @@ static void build_dict_impl(CsrMat<T>* m) {
   Ctx* c = m->ctx;
   const int64_t n = m->n_local;
   m->dict_on = false;
+  m->xwin_on = false;
   const char* e = getenv("SPB_SPMV_DICT");
   if ((e && *e == '0') || n <= 0 || n >= ((int64_t)1 << 31) - 1 || m->max_row > 64 || m->max_row < 1) return;
-  // Measured (profiles/r01_spmv_dict.txt): pays when the column stream is a third of the bytes and
-  // rows are long (27-point f64: 1.24x); 7-point rows and complex values (4 of 20 bytes) gain
-  // nothing -- their kernels are bound by the x gathers -- so they keep the plain stream.
-  // (f32: 4 of 8 bytes per non-zero are column indices, Complex32: 4 of 12 -- the same or a better ratio)
-  if (!(e && *e == '1') && (sizeof(T) > 8 || (double)m->nnz < 12.0 * (double)n)) return;
+  // Measured in round 1 (profiles/r01_spmv_dict.txt): WITHOUT the x window the dictionary pays when the
+  // column stream is a third of the bytes and rows are long (27-point f64: 1.24x); 7-point rows and
+  // complex128 values (4 of 20 bytes) gained nothing -- those kernels were bound by the x gathers.
+  // With the x window the gathers are shared-memory reads, so the decision is taken after the runs of
+  // the dictionary are known (below): window possible => dictionary on for every scalar type.
+  const bool pays_without_window = sizeof(T) <= 8 && (double)m->nnz >= 12.0 * (double)n;
+  // Measured (profiles/r02_xwin_sweep_*.txt): on B200 the window is NOT faster by default -- the 27-point
+  // kernel at 384^3 runs at 6.28 TB/s (96 % of the copy peak) with L1/L2 gathers and at 4.97 TB/s with the
+  // window (fewer resident CTAs, +34 % L2 -> SM traffic for the segments); the 7-point dictionary + window
+  // kernel ties the plain stream (0.252 vs 0.256 ms at 256^3).  So it is opt-in: SPB_SPMV_XWIN=1, or
+  // mv_hint(), whose timed candidates include it.
+  const bool window_allowed = m->xwin_want;
+  if (!(e && *e == '1') && !pays_without_window && !window_allowed) return;
   const int w = ((int)m->max_row + 7) & ~7;  // 8 offsets = two 16-byte loads per gather batch
   DevBuf keys, keys2, rows, rows2, head, run, tmp, bad;
   keys.alloc(8 * (size_t)n);
@@ -525,6 +610,24 @@ static void build_dict_impl(CsrMat<T>* m) {
   SPB_CUDA(cudaMemcpyAsync(&isbad, bad.p, 4, cudaMemcpyDeviceToHost, c->stream));
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   if (isbad) return;  // hash collision: two different rows in one run
+  // host copy of the (small) dictionary: the runs of consecutive offsets define the x window
+  m->dict_off_host.assign((size_t)(u * w), 0);
+  m->dict_len_host.assign((size_t)u, 0);
+  SPB_CUDA(cudaMemcpyAsync(m->dict_off_host.data(), doff.p, sizeof(int) * (size_t)(u * w), cudaMemcpyDeviceToHost, c->stream));
+  SPB_CUDA(cudaMemcpyAsync(m->dict_len_host.data(), dlen.p, sizeof(int) * (size_t)u, cudaMemcpyDeviceToHost, c->stream));
+  SPB_CUDA(cudaStreamSynchronize(c->stream));
+  {
+    std::vector<int> offs;
+    for (int64_t q = 0; q < u; ++q)
+      for (int k = 0; k < m->dict_len_host[q]; ++k) offs.push_back(m->dict_off_host[q * w + k]);
+    std::sort(offs.begin(), offs.end());
+    offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+    int runs = offs.empty() ? 0 : 1;
+    for (size_t k = 1; k < offs.size(); ++k) runs += offs[k] != offs[k - 1] + 1;
+    const bool window_possible = window_allowed && runs >= 1 && runs <= kMaxXwinSegs;
+    if (!(e && *e == '1') && !pays_without_window && !window_possible) return;  // keep the plain column stream
+    m->xwin_on = window_possible;  // (the layout is fixed by build_plan, which may still drop it)
+  }
   m->dict_off = std::move(doff);
   m->pid = std::move(pid);
   m->dict_w = w;
@@ -537,7 +640,8 @@ template <typename T, typename IP>
 static size_t spmv_smem_bytes(const CsrMat<T>* m) {
   const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + (m->dict_on ? 0 : align16i((m->plan_tile + 4) * 4)) +
                        align16i((m->plan_rcap + 8) * (int)sizeof(IP));
-  return m->plan_stages * stage + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(Acc<T>) + 32;
+  const size_t xw = m->dict_on && m->xwin_on ? (size_t)align16i(m->xwin_elems * (int)sizeof(T)) : 0;
+  return m->plan_stages * (stage + xw) + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(Acc<T>) + 32;
 }
 
 // Runs f(kernel_pointer) for the kernel instance selected by (halo, epi, conj).
@@ -623,22 +727,39 @@ void CsrMat<T>::analyze() {
   // ~21 KB per stage is the sweet spot; rows of <= 12 non-zeros want a 2-stage ring (the row
   // phase is short, the bulk-copy latency dominates), longer rows want 1 stage and twice the
   // resident CTAs (the row phase dominates).
-  if (ip64)
-    build_dict_impl<T, int64_t>(this);
-  else
-    build_dict_impl<T, int32_t>(this);
-  const double mean = n_local > 0 ? (double)nnz / (double)n_local : 0.0;
-  const int mean_c = (int)std::max(1.0, std::ceil(mean));
-  const int bytes_per_nnz = (int)sizeof(T) + (dict_on ? 0 : 4);
-  int ct = env_int("SPB_SPMV_CT", 0);
-  if (ct <= 0) ct = (int)((21504 / ((int64_t)mean_c * bytes_per_nnz)) / 32 * 32);
-  int stages = env_int("SPB_SPMV_STAGES", 0);
-  if (stages <= 0) stages = mean <= 12.0 ? 2 : 1;  // (also the best choice for the dictionary kernel: profiles/r01_spmv_dict.txt)
+  {
+    const char* xe = getenv("SPB_SPMV_XWIN");
+    xwin_want = xe && *xe == '1';
+  }
+  choose_format();
+  int ct, stages;
+  static_plan(ct, stages);
   build_plan(ct, stages);
   partials.alloc(sizeof(Acc<T>) * 2 * (size_t)(2 * (int64_t)c->sm_count * 32 + 2));
   red.alloc(sizeof(scal2) * 2);
   SPB_CUDA(cudaStreamSynchronize(c->stream));
   if (c->dist && !peers.empty()) classify_tiles(this);
+}
+
+// Operand format of the stream: plain CSR, column-offset dictionary, dictionary + x window (xwin_want).
+template <typename T>
+void CsrMat<T>::choose_format() {
+  if (ip64)
+    build_dict_impl<T, int64_t>(this);
+  else
+    build_dict_impl<T, int32_t>(this);
+}
+
+// The static launch-plan rule for the chosen format.
+template <typename T>
+void CsrMat<T>::static_plan(int& ct, int& stages) {
+  const double mean = n_local > 0 ? (double)nnz / (double)n_local : 0.0;
+  const int mean_c = (int)std::max(1.0, std::ceil(mean));
+  const int bytes_per_nnz = (int)sizeof(T) + (dict_on ? 0 : 4);
+  ct = env_int("SPB_SPMV_CT", 0);
+  if (ct <= 0) ct = (int)((21504 / ((int64_t)mean_c * bytes_per_nnz)) / 32 * 32);
+  stages = env_int("SPB_SPMV_STAGES", 0);
+  if (stages <= 0) stages = mean <= 12.0 ? 2 : 1;  // (also the best choice for the dictionary kernel: profiles/r01_spmv_dict.txt)
 }
 
 // Fix (consumer threads, stages), derive the tile size, cut the rows into tiles.
@@ -663,6 +784,63 @@ void CsrMat<T>::build_plan(int ct, int stages) {
   plan_rcap = std::max(64, 2 * plan_ct * rpt + 8);
   span = (max_row <= plan_tile / 2) ? (plan_tile - max_row) : plan_tile / 2;
   if (span < 1) span = 1;
+  // ---- x window: runs of consecutive column offsets -> one contiguous x segment per run and tile
+  int tile_align = 1;
+  if (dict_on && xwin_on) {
+    const int XA = std::max<int>(1, 16 / (int)sizeof(T));  // elements per 16 bytes
+    const int64_t span_w = (int64_t)plan_tile - (int64_t)XA * max_row;  // tile boundaries rounded down to XA rows
+    std::vector<int> offs;
+    for (int64_t q = 0; q < dict_u; ++q)
+      for (int k = 0; k < dict_len_host[q]; ++k) offs.push_back(dict_off_host[q * dict_w + k]);
+    std::sort(offs.begin(), offs.end());
+    offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+    std::vector<std::pair<int, int>> runs;  // (first, last) offset
+    for (int d : offs) {
+      if (!runs.empty() && d == runs.back().second + 1)
+        runs.back().second = d;
+      else
+        runs.emplace_back(d, d);
+    }
+    // rows of a typical tile: span non-zeros of mean-length rows (+ slack); shorter boundary rows give
+    // tiles with more rows, which simply fall back to global gathers
+    const int rows_typ = (int)std::min<int64_t>(4096, (int64_t)std::ceil((double)std::max<int64_t>(span_w, 1) / std::max(1.0, mean)) + 2 * XA + 8);
+    xwin_rows = (rows_typ + XA - 1) / XA * XA;
+    int acc = 0;
+    bool ok = span_w >= plan_tile / 2 && (int)runs.size() <= kMaxXwinSegs && !runs.empty();
+    if (ok) {
+      xwin_nseg = (int)runs.size();
+      for (int g = 0; g < xwin_nseg; ++g) {
+        const int gmin = runs[g].first, gmax = runs[g].second;
+        const int pad = ((gmin % XA) + XA) % XA;
+        xwin_gmin[g] = gmin;
+        xwin_pad[g] = pad;
+        xwin_extra[g] = pad + (gmax - gmin);
+        xwin_start[g] = acc;
+        acc += (xwin_extra[g] + xwin_rows + XA - 1) / XA * XA;
+      }
+      xwin_elems = acc;
+      ok = (int64_t)acc * (int64_t)sizeof(T) <= 32 * 1024 && plan_stages * (stage_bytes(tile) + (int64_t)acc * (int64_t)sizeof(T)) <= hard_cap;
+    }
+    if (ok) {
+      std::vector<int> soff((size_t)(dict_u * dict_w) + 64, 0);
+      for (int64_t q = 0; q < dict_u; ++q)
+        for (int k = 0; k < dict_len_host[q]; ++k) {
+          const int d = dict_off_host[q * dict_w + k];
+          int g = 0;
+          while (!(d >= runs[g].first && d <= runs[g].second)) ++g;
+          soff[q * dict_w + k] = xwin_start[g] + xwin_pad[g] + (d - xwin_gmin[g]);
+        }
+      dict_soff.alloc(sizeof(int) * soff.size());
+      SPB_CUDA(cudaMemcpyAsync(dict_soff.p, soff.data(), sizeof(int) * soff.size(), cudaMemcpyHostToDevice, c->stream));
+      SPB_CUDA(cudaStreamSynchronize(c->stream));
+      span = span_w;
+      tile_align = XA;
+    } else {
+      xwin_on = false;
+      xwin_nseg = 0;
+      xwin_elems = 0;
+    }
+  }
   ntiles = nnz / span + 1;
   tile_row.alloc(sizeof(int) * (size_t)(ntiles + 1));
   {
@@ -670,10 +848,10 @@ void CsrMat<T>::build_plan(int ct, int stages) {
     const int grid = (int)ceil_div(ntiles + 1, 256);
     if (ip64)
       tile_rows_kernel<int64_t><<<grid, 256, 0, c->stream>>>(bufptr<int64_t>(indptr), n_local, span,
-                                                            ntiles, bufptr<int>(tile_row));
+                                                            ntiles, bufptr<int>(tile_row), tile_align);
     else
       tile_rows_kernel<int32_t><<<grid, 256, 0, c->stream>>>(bufptr<int32_t>(indptr), n_local, span,
-                                                            ntiles, bufptr<int>(tile_row));
+                                                            ntiles, bufptr<int>(tile_row), tile_align);
     check_launch("tile_rows_kernel");
   }
   plan_bps = ip64 ? spmv_blocks_per_sm<T, int64_t>(this) : spmv_blocks_per_sm<T, int32_t>(this);
@@ -699,29 +877,44 @@ void CsrMat<T>::autotune() {
   cudaEvent_t e0, e1;
   SPB_CUDA(cudaEventCreate(&e0));
   SPB_CUDA(cudaEventCreate(&e1));
-  int best = -1;
+  // candidates: {current format, format with the x window} x {static plan, the (threads, stages) grid}.
+  // Whatever wins, the results are the same bits (every row is the CSR-order fold; exact epilogue sums).
+  int best_fmt = -1, best_ct = plan_ct, best_st = plan_stages;
   float best_ms = 0.f;
-  const int keep_ct = plan_ct, keep_st = plan_stages;
+  const bool keep_want = xwin_want;
   const int ncand = (int)(sizeof(cand) / sizeof(cand[0]));
-  for (int i = 0; i <= ncand; ++i) {
-    const int ct = i < ncand ? cand[i][0] : keep_ct, st = i < ncand ? cand[i][1] : keep_st;
-    build_plan(ct, st);
-    if (c->dist && !peers.empty()) classify_tiles(this);
-    mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
-    SPB_CUDA(cudaEventRecord(e0, c->stream));
-    for (int rep = 0; rep < 3; ++rep) mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
-    SPB_CUDA(cudaEventRecord(e1, c->stream));
-    SPB_CUDA(cudaEventSynchronize(e1));
-    float ms = 0.f;
-    SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    if (best < 0 || ms < best_ms) {
-      best = i;
-      best_ms = ms;
+  for (int fmt = 0; fmt < 2; ++fmt) {
+    xwin_want = fmt == 1;
+    choose_format();
+    if (fmt == 1 && !(dict_on && xwin_on)) break;  // no window for this matrix
+    int sct, sst;
+    static_plan(sct, sst);
+    for (int i = 0; i <= ncand; ++i) {
+      const int ct = i < ncand ? cand[i][0] : sct, st = i < ncand ? cand[i][1] : sst;
+      build_plan(ct, st);
+      if (fmt == 1 && !xwin_on) continue;  // the window did not fit this plan
+      if (c->dist && !peers.empty()) classify_tiles(this);
+      mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
+      SPB_CUDA(cudaEventRecord(e0, c->stream));
+      for (int rep = 0; rep < 3; ++rep) mul(bufptr<T>(xb), bufptr<T>(yb), EPI_NONE, nullptr, false);
+      SPB_CUDA(cudaEventRecord(e1, c->stream));
+      SPB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      if (best_fmt < 0 || ms < best_ms) {
+        best_fmt = fmt;
+        best_ct = ct;
+        best_st = st;
+        best_ms = ms;
+      }
+      if (fmt == 1) xwin_on = true;  // (build_plan clears it when the window does not fit; next candidate retries)
     }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  build_plan(best < ncand ? cand[best][0] : keep_ct, best < ncand ? cand[best][1] : keep_st);
+  xwin_want = best_fmt == 1 || (best_fmt < 0 && keep_want);
+  choose_format();
+  build_plan(best_ct, best_st);
   if (c->dist && !peers.empty()) classify_tiles(this);
 }
 
@@ -738,6 +931,21 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
     first_boundary = n_tiles_interior;
     halo_ptr = reinterpret_cast<const T*>(static_cast<char*>(halo_win->local) + kHaloHeadBytes);
   }
+  // x window of the dictionary kernels: the bulk copies need a 16-byte aligned x (a caller's odd slice is
+  // still multiplied correctly, through the global gathers); the window stays reserved in the stage
+  const bool window = dict_on && xwin_on && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  auto set_window = [&](auto& a) {
+    a.soff = bufptr<int>(dict_soff);
+    a.xw_nseg = window ? xwin_nseg : 0;
+    a.xw_rows = xwin_rows;
+    a.xw_elems = dict_on && xwin_on ? xwin_elems : 0;
+    for (int g = 0; g < kMaxXwinSegs; ++g) {
+      a.xw_gmin[g] = xwin_gmin[g];
+      a.xw_pad[g] = xwin_pad[g];
+      a.xw_extra[g] = xwin_extra[g];
+      a.xw_start[g] = xwin_start[g];
+    }
+  };
   auto run = [&](const int* list, int64_t nt, int64_t part_off) -> int64_t {
     if (nt <= 0) return 0;
     const int grid = (int)std::min<int64_t>(nt, max_grid);
@@ -747,6 +955,7 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
                              bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
                              bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
+      set_window(a);
       launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
       SpmvArgs<T, int32_t> a{bufptr<int32_t>(indptr), bufptr<int>(cols), bufptr<T>(vals), bufptr<int>(tile_row),
@@ -754,6 +963,7 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
                              bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
                              bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
+      set_window(a);
       launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
     }
     return grid;

@@ -309,8 +309,17 @@ def test_spmv_dictionary_analysis(sp, orc, monkeypatch):
     G0.mul_vec(x, y0)
     assert np.array_equal(y0, ref)
     monkeypatch.delenv("SPB_SPMV_DICT")
-    assert to_gpu(sp, orc.gen_lap3d7(10, 9, 8)).plan_info()["dictionary"] == 0        # 7 entries per row: gather bound
+    # 7 entries per row / complex values: without the x window those kernels are bound by the x gathers and
+    # keep the plain stream (round 1); with the window (shared-memory gathers) the dictionary pays for them too
+    # the x window is opt-in (SPB_SPMV_XWIN=1 or mv_hint): measured slower than L1/L2 gathers on B200
+    assert to_gpu(sp, orc.gen_lap3d7(10, 9, 8)).plan_info()["dictionary"] == 0
     assert to_gpu(sp, orc.gen_lap3d7(6, 6, 6, shift=0.5j, dtype=np.complex128)).plan_info()["dictionary"] == 0
+    assert to_gpu(sp, A).plan_info()["x_window"] == 0
+    monkeypatch.setenv("SPB_SPMV_XWIN", "1")
+    for B in (orc.gen_lap3d7(10, 9, 8), orc.gen_lap3d7(6, 6, 6, shift=0.5j, dtype=np.complex128), A):
+        pi = to_gpu(sp, B).plan_info()
+        assert pi["dictionary"] == 1 and pi["x_window"] == 1
+    monkeypatch.delenv("SPB_SPMV_XWIN")
     monkeypatch.setenv("SPB_SPMV_DICT", "1")  # forced: every row its own pattern on a random matrix
     R = _random_sorted_csr(orc, 500, 0.02, 9)
     GR = to_gpu(sp, R)
@@ -319,6 +328,62 @@ def test_spmv_dictionary_analysis(sp, orc, monkeypatch):
     yr = np.zeros(R.n)
     GR.mul_vec(xr, yr)
     assert np.array_equal(yr, orc.spmv(R, xr))
+
+
+@pytest.mark.parametrize("make", [
+    lambda o: o.gen_convdiff27(40, 37, 33),                                      # 27 runs collapse to 9 segments
+    lambda o: o.gen_lap3d7(48, 41, 37, shift=0.05),                              # 5 segments
+    lambda o: o.gen_lap3d7(31, 29, 23, shift=0.5 + 0.5j, dtype=np.complex128),   # 16-byte elements
+    lambda o: o.gen_dirichlet2d(130)[0],                                         # identity rows + 5-point rows
+    lambda o: o.gen_convdiff27(7, 5, 3),                                         # every tile touches the ends of the row range
+])
+def test_spmv_x_window(sp, orc, make, monkeypatch):
+    """x window (north star: "x held in shared memory ... via TMA where the sparsity is banded"): per tile
+    the x entries of every run of consecutive column offsets are one contiguous segment, staged in shared
+    memory by bulk copies; gathers become shared-memory reads.  Bit-identical to the sequential fold and to
+    the kernel without the window, for every launch plan, odd vector alignment (a slice starting at an odd
+    element falls back to global gathers), conjugated input and the fused epilogues."""
+    import torch
+
+    A = make(orc)
+    x = _rand_vec(A.n, A.dtype)
+    ref = orc.spmv(A, x)
+    cplx = np.iscomplexobj(x)
+    for knobs in ({}, {"SPB_SPMV_CT": "64", "SPB_SPMV_STAGES": "2"}, {"SPB_SPMV_CT": "256", "SPB_SPMV_STAGES": "1"},
+                  {"SPB_SPMV_CT": "32", "SPB_SPMV_STAGES": "3", "SPB_SPMV_MAXTILE": "512"}):
+        for k in [k for k in os.environ if k.startswith("SPB_SPMV_")]:
+            monkeypatch.delenv(k)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        monkeypatch.setenv("SPB_SPMV_XWIN", "1")
+        G = to_gpu(sp, A)
+        pi = G.plan_info()
+        assert pi["dictionary"] == 1 and pi["x_window"] == 1, pi
+        y = np.zeros(A.n, A.dtype)
+        G.mul_vec(x, y)
+        assert np.array_equal(y, ref)
+        y2 = np.zeros(A.n, A.dtype)
+        d = G.mul_vec_dot(x, y2)
+        assert np.array_equal(y2, ref)
+        dd = np.vdot(x, ref)
+        assert abs(d - (dd if cplx else dd.real)) <= 1e-12 * np.sum(np.abs(x) * np.abs(ref))
+        # device vectors at an odd element offset: no 16-byte alignment -> the same bits through global gathers
+        tdt = torch.complex128 if cplx else torch.float64
+        buf = torch.zeros(A.n + 1, dtype=tdt, device="cuda:0")
+        buf[1:] = torch.from_numpy(x).to("cuda:0")
+        out = torch.zeros(A.n, dtype=tdt, device="cuda:0")
+        torch.cuda.synchronize()
+        G.mul_vec_dev(buf.data_ptr() + buf.element_size(), out.data_ptr())
+        G.ctx.synchronize()
+        if not cplx:  # (complex128 elements are 16 bytes: every offset is aligned)
+            assert np.array_equal(out.cpu().numpy(), ref)
+    for k in [k for k in os.environ if k.startswith("SPB_SPMV_")]:
+        monkeypatch.delenv(k)
+    G0 = to_gpu(sp, A)
+    assert G0.plan_info()["x_window"] == 0
+    y0 = np.zeros(A.n, A.dtype)
+    G0.mul_vec(x, y0)
+    assert np.array_equal(y0, ref)
 
 
 @pytest.mark.parametrize("dict_knob", ["0", "1"])
