@@ -122,6 +122,18 @@ __device__ __forceinline__ void epilogue_acc(T acc, const T* w, int64_t r, Acc<T
     acc_prod(e1, cy, w[r]);  // conj_dot(t, r)
   }
 }
+// Same with the epilogue operand w[r] already in a register: the streaming row loops load it BEFORE the
+// fold, so its global-memory latency hides behind the row instead of delaying the release of the stage.
+template <typename T, int EPI>
+__device__ __forceinline__ void epilogue_acc_v(T acc, T wv, Acc<T>& e0, Acc<T>& e1) {
+  if (EPI == EPI_DOT_WY) {
+    acc_prod(e0, conj_of(wv), acc);
+  } else if (EPI == EPI_TT_TR) {
+    const T cy = conj_of(acc);
+    acc_prod(e0, cy, acc);
+    acc_prod(e1, cy, wv);
+  }
+}
 
 struct TileMeta {
   int r0, r1;     // rows of the tile
@@ -129,7 +141,7 @@ struct TileMeta {
   int ip_off;     // index of indptr[r0] inside the staged indptr slice; -1 => slice not staged
   long long s4;   // 4-aligned first non-zero
   int win;        // the stage carries the x window of this tile
-  int pad;
+  int pid_off;    // index of pid[r0] inside the staged pattern-id slice; -1 => not staged
 };
 
 __host__ __device__ inline int align16i(int v) { return (v + 15) & ~15; }
@@ -173,7 +185,8 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   const int COL_BYTES = DICT ? 0 : align16i((a.tile + 4) * 4);  // DICT: the column stream is not read at all
   const int IP_BYTES = align16i((a.rcap + 8) * (int)sizeof(IP));
   const int XW_BYTES = DICT ? align16i(a.xw_elems * (int)sizeof(T)) : 0;
-  const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES;  // vals | cols | indptr slice | x window
+  const int PID_BYTES = DICT ? align16i((a.rcap + 16) * 2) : 0;  // the tile's pattern ids (a dependent DRAM load otherwise)
+  const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES + PID_BYTES;  // vals | cols | indptr slice | x window | pattern ids
   const int STAGES = a.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
   uint64_t* empty = full + kMaxStages;
@@ -257,10 +270,14 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
             }
           }
           m.win = win ? 1 : 0;
-          m.pad = 0;
+          // pattern ids of the tile's rows: 8 ids per 16 bytes
+          const int pa = r0 & ~7;
+          const int npid = ((r1 - pa) + 7) & ~7;
+          const bool pid_ok = DICT && groups > 0 && npid <= a.rcap + 8;
+          m.pid_off = pid_ok ? (r0 - pa) : -1;
           meta[s] = m;
           const uint32_t bytes = groups * ((DICT ? 0u : 16u) + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u) +
-                                 (win ? xw_bytes : 0u);
+                                 (win ? xw_bytes : 0u) + (pid_ok ? (uint32_t)npid * 2u : 0u);
           if (bytes) {
             mbar_arrive_expect_tx(&full[s], bytes);
             if (groups) {
@@ -268,6 +285,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               if (!DICT) bulk_g2s(stage + VAL_BYTES, a.cols + s4, groups * 16u, &full[s], pol_stream);
             }
             if (ip_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES, a.indptr + ra, (uint32_t)nip * (uint32_t)sizeof(IP), &full[s], pol_stream);
+            if (pid_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES, a.pid + pa, (uint32_t)npid * 2u, &full[s], pol_stream);
             if (win) {
               unsigned char* xw = stage + VAL_BYTES + COL_BYTES + IP_BYTES;
               for (int g = 0; g < a.xw_nseg; ++g) {
@@ -283,7 +301,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           m.total = -1;  // long-row tile: consumers read it from global memory
           m.ip_off = -1;
           m.win = 0;
-          m.pad = 0;
+          m.pid_off = -1;
           meta[s] = m;
           mbar_arrive(&full[s]);
         }
@@ -305,6 +323,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
       const T* s_val = reinterpret_cast<const T*>(stage);
       const int* s_col = reinterpret_cast<const int*>(stage + VAL_BYTES);
       const IP* s_ip = reinterpret_cast<const IP*>(stage + VAL_BYTES + COL_BYTES);
+      const unsigned short* s_pid = reinterpret_cast<const unsigned short*>(stage + VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES);
       if (DICT && m.total >= 0 && m.win) {
         // x window: every operand of the tile is in shared memory -- values from the stream, x from the
         // staged segments; the same sequential fold in CSR order, no global load on the critical path
@@ -313,8 +332,11 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           int p0, p1;
           row_range(a, m, s_ip, r, p0, p1);
           T acc = zero_of<T>();
+          T wv = zero_of<T>();
+          if (EPI != EPI_NONE) wv = a.w[r];
           const int lr = r - m.r0;
-          const int4* dp = reinterpret_cast<const int4*>(a.soff + (int)a.pid[r] * a.dict_w);
+          const int pidv = m.pid_off >= 0 ? (int)s_pid[m.pid_off + lr] : (int)a.pid[r];
+          const int4* dp = reinterpret_cast<const int4*>(a.soff + pidv * a.dict_w);
           int k = p0;
           for (; k + 8 <= p1; k += 8) {
             const int4 q0 = __ldg(dp), q1 = __ldg(dp + 1);
@@ -335,7 +357,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               if (k + j < p1) acc = add(acc, mul(CONJ_IN ? conj_of(xv[j]) : xv[j], s_val[k + j]));
           }
           a.y[r] = acc;
-          epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+          epilogue_acc_v<T, EPI>(acc, wv, e0, e1);
         }
       } else if (m.total >= 0) {
         // one thread per row: x gathers go to registers (ld.global.nc through L1, L2 evict_last),
@@ -348,12 +370,18 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           int p0, p1;
           row_range(a, m, s_ip, r, p0, p1);
           T acc = zero_of<T>();
+          T wv = zero_of<T>();
+          if (EPI != EPI_NONE) wv = a.w[r];  // early: hidden behind the fold
           int k = p0;
           // DICT: the row's column offsets come from the pattern dictionary (a few KB, L1 resident;
           // neighbouring rows share the pattern, so the loads of a warp are broadcasts)
           // (dict_w is a multiple of 8 and padded with zero offsets: two 16-byte loads per batch,
           // also for the partial batch at the end of a row -- a padding entry gathers x[r])
-          const int4* dp = DICT ? reinterpret_cast<const int4*>(a.doff + (int)a.pid[r] * a.dict_w) : nullptr;
+          const int4* dp = nullptr;
+          if (DICT) {
+            const int pidv = m.pid_off >= 0 ? (int)s_pid[m.pid_off + (r - m.r0)] : (int)a.pid[r];
+            dp = reinterpret_cast<const int4*>(a.doff + pidv * a.dict_w);
+          }
           for (; k + 8 <= p1; k += 8) {
             int c[8];
             T xv[8];
@@ -389,7 +417,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               if (k + j < p1) acc = add(acc, mul(xv[j], s_val[k + j]));
           }
           a.y[r] = acc;
-          epilogue_acc<T, EPI>(acc, a.w, r, e0, e1);
+          epilogue_acc_v<T, EPI>(acc, wv, e0, e1);
         }
       } else {
         // rows up to tile/2 non-zeros keep the sequential fold (read from global memory);
@@ -641,7 +669,8 @@ static size_t spmv_smem_bytes(const CsrMat<T>* m) {
   const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + (m->dict_on ? 0 : align16i((m->plan_tile + 4) * 4)) +
                        align16i((m->plan_rcap + 8) * (int)sizeof(IP));
   const size_t xw = m->dict_on && m->xwin_on ? (size_t)align16i(m->xwin_elems * (int)sizeof(T)) : 0;
-  return m->plan_stages * (stage + xw) + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(Acc<T>) + 32;
+  const size_t pidb = m->dict_on ? (size_t)align16i((m->plan_rcap + 16) * 2) : 0;
+  return m->plan_stages * (stage + xw + pidb) + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(Acc<T>) + 32;
 }
 
 // Runs f(kernel_pointer) for the kernel instance selected by (halo, epi, conj).
@@ -781,7 +810,10 @@ void CsrMat<T>::build_plan(int ct, int stages) {
   const int max_tile = env_int("SPB_SPMV_MAXTILE", 0);
   if (max_tile > 0) tile = std::min<int64_t>(tile, std::max(256, (max_tile + 3) & ~3));
   plan_tile = (int)tile;
-  plan_rcap = std::max(64, 2 * plan_ct * rpt + 8);
+  // indptr / pattern-id entries staged per tile: a typical tile has ~ct * rpt rows; tiles of shorter
+  // (boundary) rows that exceed the capacity read their row pointers from global memory instead.  Kept
+  // tight: with the 27-point plan one KB per stage decides between 8 and 9 resident CTAs per SM.
+  plan_rcap = std::max(64, plan_ct * rpt + plan_ct * rpt / 4 + 16);
   span = (max_row <= plan_tile / 2) ? (plan_tile - max_row) : plan_tile / 2;
   if (span < 1) span = 1;
   // ---- x window: runs of consecutive column offsets -> one contiguous x segment per run and tile

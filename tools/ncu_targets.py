@@ -41,6 +41,13 @@ elif what == "c2":
 elif what == "c4":
     g = 200
     spmv(sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, g, g, g, params=(0.5, 0.5), dtype=np.complex128), g**3, torch.complex128)
+elif what == "c5xw":  # the x-window variant of the 27-point kernel (opt-in), 384^3
+    os.environ["SPB_SPMV_XWIN"] = "1"
+    g = 384
+    spmv(sp.GpuCsrMat.from_stencil(sp.STENCIL_CONVDIFF27, g, g, g, params=(1.0, 0.5, 0.25)), g**3, torch.float64)
+elif what == "c5g384":  # the default (gather) variant at the same size
+    g = 384
+    spmv(sp.GpuCsrMat.from_stencil(sp.STENCIL_CONVDIFF27, g, g, g, params=(1.0, 0.5, 0.25)), g**3, torch.float64)
 elif what == "c5f32":
     g = 384
     spmv(sp.GpuCsrMat.from_stencil(sp.STENCIL_CONVDIFF27, g, g, g, params=(1.0, 0.5, 0.25), dtype=np.float32), g**3, torch.float32)
