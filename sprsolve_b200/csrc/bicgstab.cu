@@ -16,6 +16,9 @@
 //   K3 : x -= alpha y ; x -= w z ; r -= w t ; partials of ||r||^2 and <r0,r>      (:355-362,296,301)
 // n-vector streams per iteration: K1 4R+2W, SpMV1 epilogue 1R, K2 3R+2W, SpMV2 epilogue 1R,
 // K3 6R+2W = 21 (Jacobi); 16 without preconditioner.
+#include <algorithm>
+#include <vector>
+
 #include "finalize.cuh"
 #include "solver.cuh"
 
@@ -223,11 +226,27 @@ bicg_k3(const BicgState<T>* st, int64_t n, T* x, const T* y, const T* z, T* r, c
 // multi-kernel loop above is bound by per-kernel latency (~5-12 us x 9.5 launches: 63 us on the 512^2
 // reference matrix, independent of n).  Here the WHOLE solve -- ||b||, r = A x - b, the unrolled first
 // iteration, the loop with its convergence / restart / breakdown tests, the residual history -- is ONE
-// cooperative kernel: one CTA per SM, a thread owns the same rows in every phase, phases are separated
-// by a grid barrier (one atomic + one spin per CTA) only where a vector written by other CTAs is
-// gathered (before each SpMV) or a reduction completes.  Every CTA sums the per-CTA double-double
-// partials of a reduction point itself (same fixed order, one rounding), so the Krylov scalars are
-// replicated in shared memory and no second barrier or broadcast is needed.
+// kernel: CTA b owns the contiguous rows [b R, (b+1) R), a thread owns the same rows in every phase, the
+// vectors only their owner touches live in shared memory.  An iteration has five synchronisation points
+// (three reductions, two "the gathered vector is complete"); what they cost decides the iteration time:
+//   * MODE 0 / 1 (cooperative grid, one CTA per SM): a counter barrier -- red.release.gpu arrive, ONE thread
+//     per CTA polling with relaxed loads (no acquire in the loop: an acquire invalidates the SM's L1 and with
+//     it the matrix lines), the data read afterwards at L2 (ld.cg).  A reduction point stores the CTA partial
+//     before its arrive and the first warp of EVERY CTA sums all CTA partials itself (fixed order, one
+//     rounding): the Krylov scalars are replicated, no broadcast.  Measured on B200: polling MANY addresses
+//     with relaxed (strong) loads costs ~10 clocks per load in the polling SM -- a data-as-flag exchange of
+//     the 148 partials or of the halo entries was 1.5-2x slower than counter + plain loads -- so strong
+//     accesses are kept to one flag per hand-off;
+//   * MODE 2 (banded matrices, small systems: <= 16 CTAs = ONE thread-block cluster, launched with the
+//     non-portable cluster size 16): nothing of an iteration leaves the SMs.  A CTA keeps the window
+//     [row0 - bw_lo, row1 + bw_hi) of the gathered vector (y = M p, then z = M s) AND its slice of the matrix
+//     in shared memory; the exchanges go through DISTRIBUTED SHARED MEMORY -- the hardware cluster barrier
+//     instead of L2 round trips, reduction partials pushed into every CTA's inbox with st.shared::cluster,
+//     halo entries read from the neighbours' windows with ld.shared::cluster.  This is the path of the
+//     reference's own bench sizes (100^2 .. 140^2).
+//   Also measured and dropped: the same window with a per-CTA release flag and L2 halo loads on the full grid
+//   (three dependent L2 round trips per hand-off: slower than the counter barrier + L2 gathers, 30.7 vs 23.9 us
+//   per iteration on 512^2) and register double-buffering of the next row's matrix entries (spills at 512 threads).
 // Same element-wise operations and exactly rounded sums as the multi-kernel path => the same bits.
 template <typename T>
 struct FusedArgs {
@@ -239,19 +258,64 @@ struct FusedArgs {
   T *x, *r, *r0, *p, *y, *v, *t, *z;
   const void* dinv;
   BicgState<T>* st;         // final state (written by CTA 0)
-  Acc<T>* parts;            // [3][2 * gridDim.x]
+  double* rslots;           // [3][gridDim.x][2 * sizeof(Acc<T>) / 8] reduction slots (data-as-flag)
   unsigned long long* bar;  // grid barrier counter, zeroed before the launch
   double* hist;
   long long cap, max_iter;
   double tol;
   long long* stats;  // optional (SPB_FUSED_STATS=1): clocks of CTA 0 per phase, see the lap() calls
-  int slots_per_thread;  // ceil(n / threads of the grid): shared-memory slots a thread needs per vector
+  int slots_per_thread;  // ceil(rows_per_cta / BLOCK): shared-memory slots a thread needs per vector
   unsigned poll_sleep;   // ns between two polls of the grid barrier (0: spin)
+  int rows_per_cta;      // R
+  int bw_lo, bw_hi;      // max (row - col), max (col - row) over the matrix (MODE 2)
+  int win_elems;         // capacity of the shared-memory window (MODE 2)
+  int mat_cap;           // MODE 2: matrix entries of a CTA's rows that fit its shared memory (0: matrix stays in global memory)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// ---- thread-block cluster / distributed shared memory (MODE 3)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local_smem, unsigned rank) {  // the same variable in CTA `rank`
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_smem);
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ void dsmem_st2(uint32_t ra, double a, double b) {
+  asm volatile("st.shared::cluster.v2.f64 [%0], {%1,%2};" ::"r"(ra), "d"(a), "d"(b) : "memory");
+}
+__device__ __forceinline__ double dsmem_ld(uint32_t ra, const double*) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ cplx dsmem_ld(uint32_t ra, const cplx*) {
+  cplx v;
+  asm volatile("ld.shared::cluster.v2.f64 {%0,%1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ float dsmem_ld(uint32_t ra, const float*) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ cplxf dsmem_ld(uint32_t ra, const cplxf*) {
+  cplxf v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(v.re), "=f"(v.im) : "r"(ra) : "memory");
   return v;
 }
 // vectors other CTAs write during the kernel are read at L2 (the L1 of an SM is not coherent)
@@ -260,6 +324,10 @@ __device__ __forceinline__ cplx ld_l2(const cplx* p) {
   const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
   return cplx{v.x, v.y};
 }
+__device__ __forceinline__ void st_l2(double* p, double v) { __stcg(p, v); }
+__device__ __forceinline__ void st_l2(cplx* p, cplx v) { __stcg(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
+__device__ __forceinline__ void st_l2(float* p, float v) { __stcg(p, v); }
+__device__ __forceinline__ void st_l2(cplxf* p, cplxf v) { __stcg(reinterpret_cast<float2*>(p), make_float2(v.re, v.im)); }
 __device__ __forceinline__ double ld_ro(const double* p) { return __ldg(p); }
 __device__ __forceinline__ cplx ld_ro(const cplx* p) {
   const double2 v = __ldg(reinterpret_cast<const double2*>(p));
@@ -275,14 +343,6 @@ __device__ __forceinline__ cplxf ld_ro(const cplxf* p) {
   const float2 v = __ldg(reinterpret_cast<const float2*>(p));
   return cplxf{v.x, v.y};
 }
-__device__ __forceinline__ AccR ld_l2(const AccR* p) {
-  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-  return AccR{v.x, v.y};
-}
-__device__ __forceinline__ AccC ld_l2(const AccC* p) {
-  const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
-  return AccC{a.x, a.y, b.x, b.y};
-}
 template <typename T>
 __device__ __forceinline__ scal2 acc_round(const AccR& a) {
   return scal2{round_to_real<T>(a.hi + a.lo), 0.0};
@@ -291,6 +351,29 @@ template <typename T>
 __device__ __forceinline__ scal2 acc_round(const AccC& a) {
   return scal2{round_to_real<T>(a.rh + a.rl), round_to_real<T>(a.ih + a.il)};
 }
+
+// CTA partials of a reduction point in global memory (MODE 0-2): written before the arrive, read at L2 after it
+__device__ __forceinline__ void slot_st(double* p, const AccR& a) { __stcg(reinterpret_cast<double2*>(p), make_double2(a.hi, a.lo)); }
+__device__ __forceinline__ void slot_st(double* p, const AccC& a) {
+  __stcg(reinterpret_cast<double2*>(p), make_double2(a.rh, a.rl));
+  __stcg(reinterpret_cast<double2*>(p) + 1, make_double2(a.ih, a.il));
+}
+__device__ __forceinline__ void slot_ld(const double* p, AccR& a) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  a = AccR{v.x, v.y};
+}
+__device__ __forceinline__ void slot_ld(const double* p, AccC& a) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p)), w = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+  a = AccC{v.x, v.y, w.x, w.y};
+}
+// the same through (distributed) shared memory (MODE 3)
+__device__ __forceinline__ void dslot_st(uint32_t ra, const AccR& a) { dsmem_st2(ra, a.hi, a.lo); }
+__device__ __forceinline__ void dslot_st(uint32_t ra, const AccC& a) {
+  dsmem_st2(ra, a.rh, a.rl);
+  dsmem_st2(ra + 16, a.ih, a.il);
+}
+__device__ __forceinline__ void sslot_ld(const double* p, AccR& a) { a = AccR{p[0], p[1]}; }
+__device__ __forceinline__ void sslot_ld(const double* p, AccC& a) { a = AccC{p[0], p[1], p[2], p[3]}; }
 
 // One CSR row folded sequentially in CSR order (src/mat.rs:100-105); matrix through the read-only path
 // (constant for the whole kernel, L1-resident after the first iteration), x at L2.  Gathers are issued
@@ -315,7 +398,6 @@ __device__ __forceinline__ T fused_row(const FusedArgs<T>& a, int p0, int p1, co
   }
   return acc;
 }
-
 // the next own row's column / value lines into L1 while the current row waits for its gathers
 template <typename T>
 __device__ __forceinline__ void fused_prefetch_row(const FusedArgs<T>& a, int p0, int p1) {
@@ -328,25 +410,82 @@ __device__ __forceinline__ void fused_prefetch_row(const FusedArgs<T>& a, int p0
 __device__ __forceinline__ void red_release_gpu_add(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// sum of the first N (a power of two <= 32) lanes; valid in lane 0
+template <int N, typename A>
+__device__ __forceinline__ A warp_sum_n(A v) {
+#pragma unroll
+  for (int d = N / 2; d > 0; d >>= 1) v = add(v, shfl_down(v, d));
+  return v;
+}
 
-// SV: the vectors only their owning thread touches (r, r0, p, v, t, 1/diag) live in SHARED MEMORY for the
-// whole solve -- a thread owns rows gtid + k * nth, slot k * BLOCK + tid -- so the vector-update phases
-// never wait for L2 (~1000 clocks per dependent access under this load); only what other CTAs gather
-// (y, z) and x go to global memory.  Falls back to global vectors (SV = false) when the slots do not fit.
-template <typename T, typename V, bool PC, int BLOCK, bool SV>
+__device__ __forceinline__ AccR shfl_idx(AccR v, int src) {
+  return AccR{__shfl_sync(0xffffffffu, v.hi, src), __shfl_sync(0xffffffffu, v.lo, src)};
+}
+__device__ __forceinline__ AccC shfl_idx(AccC v, int src) {
+  return AccC{__shfl_sync(0xffffffffu, v.rh, src), __shfl_sync(0xffffffffu, v.rl, src), __shfl_sync(0xffffffffu, v.ih, src),
+              __shfl_sync(0xffffffffu, v.il, src)};
+}
+
+static const int kFusedMaxGrid = 160;  // slots a lane of the summing warp handles: kFusedMaxGrid / 32
+static const int kFusedCluster = 16;   // MODE 2: CTAs of the one cluster (non-portable size, B200 allows 16)
+
+// Cluster mode SpMV over the own rows: x from the shared-memory window, and the matrix slice of the CTA from
+// shared memory too when it fits (columns stored window-relative) -- nothing in the row loop leaves the SM.
+// (The cluster barrier flushes L1, so a matrix left in global memory would be re-read from L2 in every phase.)
+template <typename T, int BLOCK, typename F>
+__device__ __forceinline__ void fused_spmv_win(const FusedArgs<T>& a, const int2* ext, int nrows, int row0, const T* win, int wlo,
+                                               const int* mcols, const T* mvals, int mbase, bool mat_smem, F&& emit) {
+  for (int l = threadIdx.x; l < nrows; l += BLOCK) {
+    const int2 e = ext[l];
+    T acc = zero_of<T>();
+    if (mat_smem) {
+      for (int k = e.x - mbase; k < e.y - mbase; ++k) acc = add(acc, mul(win[mcols[k]], mvals[k]));
+    } else {
+      for (int k = e.x; k < e.y; k += 8) {
+        int c[8];
+        T m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kk = min(k + j, e.y - 1);
+          c[j] = __ldg(a.cols + kk);
+          m[j] = ld_ro(a.vals + kk);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (k + j < e.y) acc = add(acc, mul(win[c[j] - wlo], m[j]));
+      }
+    }
+    emit(l, row0 + l, acc);
+  }
+}
+
+// MODE 0: all vectors in global memory, counter barrier before each SpMV.
+// MODE 1: the vectors only their owning thread touches (r, r0, p, v, t, x, 1/diag, row extents) live in
+//         SHARED MEMORY for the whole solve (slot = local row), so the vector-update phases never wait for
+//         L2; y and z go to global memory, counter barrier before each SpMV.
+// MODE 2: MODE 1 inside ONE thread-block cluster (banded matrices, small systems): the window of the gathered
+//         vector and the matrix slice in shared memory, all exchanges through distributed shared memory.
+template <typename T, typename V, bool PC, int BLOCK, int MODE>
 __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T> a) {
+  constexpr bool SV = MODE >= 1, WIN = MODE == 2, CL = MODE == 2;
   constexpr int NW = BLOCK / 32;
+  constexpr int AW = (int)sizeof(Acc<T>) / 8;  // doubles per accumulator
+  constexpr int MAXS = kFusedMaxGrid / 32;
   extern __shared__ __align__(16) unsigned char fused_smem[];
   __shared__ BicgState<T> S;
   __shared__ Acc<T> wsum[2][NW];
+  __shared__ __align__(16) double inbox[2][kFusedCluster][2 * AW];  // MODE 2: the CTA partials of a reduction point
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int gtid = blockIdx.x * BLOCK + tid, nth = gridDim.x * BLOCK, n = a.n;
+  const int n = a.n, G = (int)gridDim.x;
+  const int R = a.rows_per_cta;
+  const int row0 = min(n, (int)blockIdx.x * R), row1 = min(n, row0 + R);
+  const int nrows = row1 - row0;
   const V* dinv_g = static_cast<const V*>(a.dinv);
   double* hist = blockIdx.x == 0 ? a.hist : nullptr;  // one writer
-  unsigned long long target = 0;
-  int rp = 0;  // reduction points cycle through three partial buffers (a buffer is re-written two barriers later)
+  unsigned long long target = 0;  // arrivals the barrier counter must have seen at the next sync point
+  int rp = 0;  // reduction points cycle through three slot buffers (two inboxes in MODE 3)
   scal2 red[2];
-  // own-row vectors: shared memory (slot = k * BLOCK + tid) or global (index = row)
+  // own-row vectors: shared memory (slot = local row) or global (index = row)
   const int slots = a.slots_per_thread * BLOCK;
   T* const sm = reinterpret_cast<T*>(fused_smem);
   T* const r_v = SV ? sm : a.r;
@@ -354,42 +493,63 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
   T* const p_v = SV ? sm + 2 * slots : a.p;
   T* const v_v = SV ? sm + 3 * slots : a.v;
   T* const t_v = SV ? sm + 4 * slots : a.t;
-  const V* const d_v = SV ? reinterpret_cast<const V*>(sm + 5 * slots) : dinv_g;
-  // row extents of the own rows (shared memory: one dependent L2 round trip less per SpMV row)
-  const int2* const ext_v = reinterpret_cast<const int2*>(fused_smem + (size_t)slots * (5 * sizeof(T) + (PC ? sizeof(V) : 0)));
-  auto extent = [&](int k, int i) -> int2 {
-    if (SV) return ext_v[k * BLOCK + tid];
+  T* const x_v = SV ? sm + 5 * slots : a.x;
+  const size_t off_d = (size_t)slots * 6 * sizeof(T);
+  const size_t off_e = off_d + (PC ? (size_t)slots * sizeof(V) : 0);
+  const size_t off_w = (off_e + (size_t)slots * sizeof(int2) + 15) & ~(size_t)15;
+  const V* const d_v = SV ? reinterpret_cast<const V*>(fused_smem + off_d) : dinv_g;
+  const int2* const ext_v = reinterpret_cast<const int2*>(fused_smem + off_e);
+  // window of the gathered vector: columns [wlo, whi)
+  const int wlo = WIN ? max(0, row0 - a.bw_lo) : 0, whi = WIN ? min(n, row1 + a.bw_hi) : 0;
+  T* const win = reinterpret_cast<T*>(fused_smem + off_w);
+  const int nlo = row0 - wlo, nhi = whi - row1;  // halo entries below / above the own rows
+  // matrix slice of the own rows in shared memory (cluster mode, when it fits): columns window-relative
+  const size_t off_mc = (off_w + (size_t)a.win_elems * sizeof(T) + 15) & ~(size_t)15;
+  const size_t off_mv = (off_mc + (size_t)a.mat_cap * sizeof(int) + 15) & ~(size_t)15;
+  int* const mcols = reinterpret_cast<int*>(fused_smem + off_mc);
+  T* const mvals = reinterpret_cast<T*>(fused_smem + off_mv);
+  const int mbase = WIN ? __ldg(a.indptr + row0) : 0;
+  const bool mat_smem = WIN && a.mat_cap > 0 && (__ldg(a.indptr + row1) - mbase) <= a.mat_cap;
+  auto extent = [&](int l, int i) -> int2 {
+    if (SV) return ext_v[l];
     return make_int2(__ldg(a.indptr + i), __ldg(a.indptr + i + 1));
   };
-#define SPB_OWN(k, i) (SV ? (k) * BLOCK + tid : (i))
-#define SPB_ROWS(k, i) for (int k = 0, i = gtid; i < n; ++k, i += nth)
+#define SPB_OWN(l, i) (SV ? (l) : (i))
+#define SPB_ROWS(l, i) for (int l = tid, i = row0 + tid; l < nrows; l += BLOCK, i += BLOCK)
   long long t_last = a.stats ? clock64() : 0;
   long long t_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  auto lap = [&](int k) {  // diagnostics: phase clocks of CTA 0 (accumulated in registers, stored at the end)
-    if (a.stats && blockIdx.x == 0 && tid == 0) {
+  auto lap = [&](int k) {  // diagnostics: phase clocks per CTA (accumulated in registers, stored at the end)
+    if (a.stats && tid == 0) {
       const long long now = clock64();
       t_acc[k] += now - t_last;
       t_last = now;
     }
   };
 
-  // Grid barrier: a release-add without return value (the arriving thread does not wait for the round
-  // trip) and an acquire spin by one thread per CTA; __syncthreads on both sides extends the ordering to
-  // the whole CTA.
-  auto grid_sync = [&]() {
-    __syncthreads();
-    if (tid == 0) {
-      target += gridDim.x;
-      red_release_gpu_add(a.bar, 1ULL);
-      while (ld_acquire_gpu_u64(a.bar) < target) {
-        if (a.poll_sleep) __nanosleep(a.poll_sleep);
-      }
+  // Barrier over all CTAs.  Grid: a release-add without return value and a relaxed spin by one thread per CTA
+  // (what is read afterwards is read at L2); __syncthreads on both sides extends the ordering to the CTA.
+  // Cluster: the hardware barrier (release / acquire at cluster scope, shared and global memory).
+  auto arrive_and_wait = [&]() {  // thread 0 only
+    target += gridDim.x;
+    red_release_gpu_add(a.bar, 1ULL);
+    while (ld_relaxed_gpu_u64(a.bar) < target) {
+      if (a.poll_sleep) __nanosleep(a.poll_sleep);
     }
-    __syncthreads();
   };
-  // A reduction point.  Block partial: warp shuffles, one shared-memory hop, the first warp folds the
-  // warps; after the barrier the FIRST WARP of every CTA sums all CTA partials itself (fixed order, both
-  // slots interleaved) and rounds once: red[] lands in the registers of thread 0, identical in every CTA.
+  auto grid_sync = [&]() {
+    if (CL) {
+      cluster_sync_all();
+    } else {
+      __syncthreads();
+      if (tid == 0) arrive_and_wait();
+      __syncthreads();
+    }
+  };
+  // A reduction point.  Block partial: warp shuffles, one shared-memory hop, the first warp folds the warps.
+  // Grid: lane 0 stores the CTA partial into its slot and arrives; after the counter has seen every CTA the
+  // FIRST WARP of every CTA sums all slots itself (fixed order, both sums interleaved) and rounds once.
+  // Cluster: the partial is pushed into every CTA's inbox, then the cluster barrier.
+  // red[] lands in the registers of thread 0, identical in every CTA.
   auto reduce = [&](Acc<T> e0, Acc<T> e1, bool two) {
     e0 = warp_sum(e0);
     if (two) e1 = warp_sum(e1);
@@ -398,47 +558,102 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
       wsum[1][wid] = e1;
     }
     __syncthreads();
-    Acc<T>* pb = a.parts + (size_t)rp * 2 * gridDim.x;
+    Acc<T> b0 = zero_of<Acc<T>>(), b1 = zero_of<Acc<T>>();
     if (wid == 0) {
-      Acc<T> b0 = lane < NW ? wsum[0][lane] : zero_of<Acc<T>>();
-      Acc<T> b1 = lane < NW ? wsum[1][lane] : zero_of<Acc<T>>();
-      b0 = warp_sum(b0);
-      if (two) b1 = warp_sum(b1);
-      if (lane == 0) {
-        pb[2 * blockIdx.x] = b0;
-        pb[2 * blockIdx.x + 1] = b1;
-      }
+      b0 = lane < NW ? wsum[0][lane] : zero_of<Acc<T>>();
+      b1 = lane < NW ? wsum[1][lane] : zero_of<Acc<T>>();
+      b0 = warp_sum_n<NW>(b0);
+      if (two) b1 = warp_sum_n<NW>(b1);
     }
-    lap(5);  // block partial
-    grid_sync();
-    lap(6);  // barrier of a reduction point
-    if (wid == 0) {
-      Acc<T> g0 = zero_of<Acc<T>>(), g1 = zero_of<Acc<T>>();
-      for (int i = lane; i < (int)gridDim.x; i += 32) {
-        g0 = add(g0, ld_l2(pb + 2 * i));
-        if (two) g1 = add(g1, ld_l2(pb + 2 * i + 1));
+    if (CL) {
+      const int par = rp & 1;
+      if (wid == 0) {
+        b0 = shfl_idx(b0, 0);
+        b1 = shfl_idx(b1, 0);
+        if (lane < G) {
+          const uint32_t ra = dsmem_addr(&inbox[par][blockIdx.x][0], (unsigned)lane);
+          dslot_st(ra, b0);
+          dslot_st(ra + 8 * AW, b1);
+        }
       }
-      g0 = warp_sum(g0);
-      if (two) g1 = warp_sum(g1);
-      red[0] = acc_round<T>(g0);
-      red[1] = acc_round<T>(g1);  // (valid in lane 0 = thread 0, the only consumer)
+      lap(5);  // block partial
+      cluster_sync_all();
+      lap(6);  // waiting for the other CTAs
+      if (wid == 0) {
+        Acc<T> g0 = zero_of<Acc<T>>(), g1 = zero_of<Acc<T>>();
+        if (lane < G) {
+          sslot_ld(&inbox[par][lane][0], g0);
+          sslot_ld(&inbox[par][lane][AW], g1);
+        }
+        g0 = warp_sum_n<kFusedCluster>(g0);
+        if (two) g1 = warp_sum_n<kFusedCluster>(g1);
+        red[0] = acc_round<T>(g0);
+        red[1] = acc_round<T>(g1);
+      }
+      rp ^= 1;
+    } else {
+      double* const buf = a.rslots + (size_t)rp * G * 2 * AW;
+      if (tid == 0) {
+        slot_st(buf + (size_t)blockIdx.x * 2 * AW, b0);
+        slot_st(buf + (size_t)blockIdx.x * 2 * AW + AW, b1);
+        lap(5);  // block partial
+        arrive_and_wait();
+        lap(6);  // waiting for the other CTAs
+      }
+      if (wid == 0) {
+        __syncwarp();
+        Acc<T> g0 = zero_of<Acc<T>>(), g1 = zero_of<Acc<T>>();
+#pragma unroll
+        for (int k = 0; k < MAXS; ++k) {
+          const int i = lane + 32 * k;
+          if (i < G) {
+            Acc<T> q0, q1;
+            slot_ld(buf + (size_t)i * 2 * AW, q0);
+            g0 = add(g0, q0);
+            if (two) {
+              slot_ld(buf + (size_t)i * 2 * AW + AW, q1);
+              g1 = add(g1, q1);
+            }
+          }
+        }
+        g0 = warp_sum(g0);
+        if (two) g1 = warp_sum(g1);
+        red[0] = acc_round<T>(g0);
+        red[1] = acc_round<T>(g1);  // (valid in lane 0 = thread 0, the only consumer)
+      }
+      rp = rp == 2 ? 0 : rp + 1;
     }
-    rp = rp == 2 ? 0 : rp + 1;
     lap(7);  // sum of the CTA partials
+  };
+  // The own part of the gathered vector is written (window + the rows the neighbours need in global memory, or
+  // the whole vector in MODE 0 / 1): wait until what this CTA gathers from the others is there.
+  auto gather_ready = [&]() {
+    if (CL) {
+      cluster_sync_all();  // every CTA's own part is in its window
+      for (int h = tid; h < nlo + nhi; h += BLOCK) {
+        const int j = h < nlo ? wlo + h : row1 + (h - nlo);
+        const int owner = j / R;
+        const int owlo = max(0, owner * R - a.bw_lo);
+        win[j - wlo] = dsmem_ld(dsmem_addr(win + (j - owlo), (unsigned)owner), (const T*)nullptr);
+      }
+      __syncthreads();
+    } else {
+      grid_sync();
+    }
   };
   // r = A x - rhs ; r0 = r ; ||r||^2   (:243-251, and the restart :305-316)
   auto residual = [&](int restart) {
+    if (SV && restart) {  // x lives in shared memory: the neighbours gather it from global memory
+      SPB_ROWS(l, i) st_l2(a.x + i, x_v[l]);
+      grid_sync();
+    }
     Acc<T> e0 = zero_of<Acc<T>>();
     const T m1 = neg(one_of<T>());
-    SPB_ROWS(k, i) {
-      const int2 e = extent(k, i);
-      if (SV && i + nth < n) {
-        const int2 en = extent(k + 1, i + nth);
-        fused_prefetch_row(a, en.x, en.y);
-      }
+    SPB_ROWS(l, i) {
+      const int2 e = extent(l, i);
       const T ri = add(fused_row(a, e.x, e.y, a.x), mul(a.rhs[i], m1));
-      r_v[SPB_OWN(k, i)] = ri;
-      r0_v[SPB_OWN(k, i)] = ri;
+      r_v[SPB_OWN(l, i)] = ri;
+      r0_v[SPB_OWN(l, i)] = ri;
       acc_sq(e0, ri);
     }
     reduce(e0, zero_of<Acc<T>>(), false);
@@ -447,10 +662,10 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
   };
   // everything of an iteration after the S1 test; returns false when the solve ended (breakdown)
   auto iteration = [&](bool first) -> bool {
-    {  // K1: p, y = M p (y is what the other CTAs gather)
+    {  // K1: p, y = M p (y is what the SpMV gathers)
       const T c_pv = S.c_pv, beta = S.beta, one = one_of<T>();
-      SPB_ROWS(k, i) {
-        const int o = SPB_OWN(k, i);
+      SPB_ROWS(l, i) {
+        const int o = SPB_OWN(l, i);
         T pi;
         if (first) {
           pi = r_v[o];
@@ -459,28 +674,40 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
           pi = add(pi, mul(r_v[o], one));
         }
         p_v[o] = pi;
-        a.y[i] = PC ? mul_diag(pi, d_v[o]) : pi;
+        const T yi = PC ? mul_diag(pi, d_v[o]) : pi;
+        if (WIN) {
+          win[i - wlo] = yi;
+        } else {
+          a.y[i] = yi;
+        }
       }
-      if (SV && gtid < n) {  // first row of the SpMV that follows the barrier
-        const int2 e0 = extent(0, gtid);
+      if (SV && !WIN && tid < nrows) {  // first row of the SpMV that follows the barrier
+        const int2 e0 = extent(tid, row0 + tid);
         fused_prefetch_row(a, e0.x, e0.y);
       }
     }
     lap(0);  // K1
-    grid_sync();  // y complete
-    lap(8);  // plain barrier
+    gather_ready();
+    lap(8);  // y of the neighbours / plain barrier
     {  // v = A y, <r0, v>
       Acc<T> e0 = zero_of<Acc<T>>();
-      SPB_ROWS(k, i) {
-        const int o = SPB_OWN(k, i);
-        const int2 e = extent(k, i);
-        if (SV && i + nth < n) {
-          const int2 en = extent(k + 1, i + nth);
-          fused_prefetch_row(a, en.x, en.y);
+      if (WIN) {
+        fused_spmv_win<T, BLOCK>(a, ext_v, nrows, row0, win, wlo, mcols, mvals, mbase, mat_smem, [&](int l, int, T vi) {
+          v_v[l] = vi;
+          acc_prod(e0, conj_of(r0_v[l]), vi);
+        });
+      } else {
+        SPB_ROWS(l, i) {
+          const int o = SPB_OWN(l, i);
+          const int2 e = extent(l, i);
+          if (SV && l + BLOCK < nrows) {
+            const int2 en = extent(l + BLOCK, i + BLOCK);
+            fused_prefetch_row(a, en.x, en.y);
+          }
+          const T vi = fused_row(a, e.x, e.y, a.y);
+          v_v[o] = vi;
+          acc_prod(e0, conj_of(r0_v[o]), vi);
         }
-        const T vi = fused_row(a, e.x, e.y, a.y);
-        v_v[o] = vi;
-        acc_prod(e0, conj_of(r0_v[o]), vi);
       }
       lap(1);  // SpMV 1
       reduce(e0, zero_of<Acc<T>>(), false);
@@ -491,34 +718,48 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     if (S.h.status != DS_RUNNING) return false;
     {  // K2: r -= alpha v, z = M r
       const T nalpha = S.nalpha;
-      SPB_ROWS(k, i) {
-        const int o = SPB_OWN(k, i);
+      SPB_ROWS(l, i) {
+        const int o = SPB_OWN(l, i);
         const T ri = add(r_v[o], mul(v_v[o], nalpha));
         r_v[o] = ri;
-        a.z[i] = PC ? mul_diag(ri, d_v[o]) : ri;
+        const T zi = PC ? mul_diag(ri, d_v[o]) : ri;
+        if (WIN) {
+          win[i - wlo] = zi;
+        } else {
+          a.z[i] = zi;
+        }
       }
-      if (SV && gtid < n) {
-        const int2 e0 = extent(0, gtid);
+      if (SV && !WIN && tid < nrows) {
+        const int2 e0 = extent(tid, row0 + tid);
         fused_prefetch_row(a, e0.x, e0.y);
       }
     }
     lap(2);  // K2
-    grid_sync();  // z complete
+    gather_ready();
     lap(8);
     {  // t = A z, <t,t>, <t,r>
       Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
-      SPB_ROWS(k, i) {
-        const int o = SPB_OWN(k, i);
-        const int2 e = extent(k, i);
-        if (SV && i + nth < n) {
-          const int2 en = extent(k + 1, i + nth);
-          fused_prefetch_row(a, en.x, en.y);
+      if (WIN) {
+        fused_spmv_win<T, BLOCK>(a, ext_v, nrows, row0, win, wlo, mcols, mvals, mbase, mat_smem, [&](int l, int, T ti) {
+          t_v[l] = ti;
+          const T cy = conj_of(ti);
+          acc_prod(e0, cy, ti);
+          acc_prod(e1, cy, r_v[l]);
+        });
+      } else {
+        SPB_ROWS(l, i) {
+          const int o = SPB_OWN(l, i);
+          const int2 e = extent(l, i);
+          if (SV && l + BLOCK < nrows) {
+            const int2 en = extent(l + BLOCK, i + BLOCK);
+            fused_prefetch_row(a, en.x, en.y);
+          }
+          const T ti = fused_row(a, e.x, e.y, a.z);
+          t_v[o] = ti;
+          const T cy = conj_of(ti);
+          acc_prod(e0, cy, ti);
+          acc_prod(e1, cy, r_v[o]);
         }
-        const T ti = fused_row(a, e.x, e.y, a.z);
-        t_v[o] = ti;
-        const T cy = conj_of(ti);
-        acc_prod(e0, cy, ti);
-        acc_prod(e1, cy, r_v[o]);
       }
       lap(3);  // SpMV 2
       reduce(e0, e1, true);
@@ -527,17 +768,17 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     __syncthreads();
     lap(9);
     {  // K3 + the partials of the next iteration's test.  y_i, z_i of the own rows are recomputed from p and r
-       // (the same single operation on the same operands: the same bits) instead of re-read from global.
+       // (the same single operation on the same operands: the same bits) instead of re-read from memory.
       Acc<T> e0 = zero_of<Acc<T>>(), e1 = zero_of<Acc<T>>();
       const T nalpha = S.nalpha, nw = S.nw;
-      SPB_ROWS(k, i) {
-        const int o = SPB_OWN(k, i);
+      SPB_ROWS(l, i) {
+        const int o = SPB_OWN(l, i);
         const T pi = p_v[o], si = r_v[o];
         const T yi = PC ? mul_diag(pi, d_v[o]) : pi;
         const T zi = PC ? mul_diag(si, d_v[o]) : si;
-        T xi = add(a.x[i], mul(yi, nalpha));
+        T xi = add(x_v[o], mul(yi, nalpha));
         xi = add(xi, mul(zi, nw));
-        a.x[i] = xi;
+        x_v[o] = xi;
         const T ri = add(si, mul(t_v[o], nw));
         r_v[o] = ri;
         acc_sq(e0, ri);
@@ -554,24 +795,33 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
     S.h.status = DS_RUNNING;
     S.tol = (real_t<T>)a.tol;
   }
-  if (SV) {  // row extents and 1 / diag of the own rows
-    int2* ew = reinterpret_cast<int2*>(fused_smem + (size_t)slots * (5 * sizeof(T) + (PC ? sizeof(V) : 0)));
-    V* dw = reinterpret_cast<V*>(sm + 5 * slots);
-    SPB_ROWS(k, i) {
-      ew[k * BLOCK + tid] = make_int2(__ldg(a.indptr + i), __ldg(a.indptr + i + 1));
-      if (PC) dw[k * BLOCK + tid] = dinv_g[i];
+  if (SV) {  // row extents, 1 / diag and x of the own rows
+    int2* ew = reinterpret_cast<int2*>(fused_smem + off_e);
+    V* dw = reinterpret_cast<V*>(fused_smem + off_d);
+    SPB_ROWS(l, i) {
+      ew[l] = make_int2(__ldg(a.indptr + i), __ldg(a.indptr + i + 1));
+      if (PC) dw[l] = dinv_g[i];
+      x_v[l] = a.x[i];
     }
   }
+  if (mat_smem) {
+    const int cnt = __ldg(a.indptr + row1) - mbase;
+    for (int k = tid; k < cnt; k += BLOCK) {
+      mcols[k] = __ldg(a.cols + mbase + k) - wlo;
+      mvals[k] = ld_ro(a.vals + mbase + k);
+    }
+  }
+  if (CL) cluster_sync_all();  // every CTA of the cluster runs before its shared memory is addressed
   __syncthreads();
   {  // ||b||  (:225-231)
     Acc<T> e0 = zero_of<Acc<T>>();
-    for (int i = gtid; i < n; i += nth) acc_sq(e0, a.rhs[i]);
+    SPB_ROWS(l, i) acc_sq(e0, a.rhs[i]);
     reduce(e0, zero_of<Acc<T>>(), false);
     if (tid == 0) bicg_s_rhs_body(&S, red);
     __syncthreads();
   }
   if (S.h.status == DS_ZERO_RHS) {
-    for (int i = gtid; i < n; i += nth) a.x[i] = zero_of<T>();
+    SPB_ROWS(l, i) x_v[SPB_OWN(l, i)] = zero_of<T>();
   } else {
     residual(0);
     if (S.h.status == DS_RUNNING && iteration(true)) {
@@ -585,13 +835,26 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
       }
     }
   }
-  if (blockIdx.x == 0 && tid == 0) {
-    *a.st = S;
-    if (a.stats)
-      for (int k = 0; k < 10; ++k) a.stats[k] = t_acc[k];
-  }
+  if (SV) SPB_ROWS(l, i) a.x[i] = x_v[l];
+  if (blockIdx.x == 0 && tid == 0) *a.st = S;
+  if (a.stats && tid == 0)
+    for (int k = 0; k < 10; ++k) a.stats[10 * blockIdx.x + k] = t_acc[k];
+  if (CL) cluster_sync_all();  // no CTA leaves while its shared memory may still be read
 #undef SPB_OWN
 #undef SPB_ROWS
+}
+
+// max (row - col) and max (col - row): the reach of the gathers below / above the diagonal
+__global__ void fused_band_kernel(const int* indptr, const int* cols, int n, int* out) {
+  int lo = 0, hi = 0;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x)
+    for (int k = indptr[r]; k < indptr[r + 1]; ++k) {
+      const int c = cols[k];
+      lo = max(lo, r - c);
+      hi = max(hi, c - r);
+    }
+  if (lo) atomicMax(out, lo);  // integer atomics: order-independent
+  if (hi) atomicMax(out + 1, hi);
 }
 
 // ---------------------------------------------------------------- host driver
@@ -602,7 +865,8 @@ struct BicgStab : spb_solver {
   DevBuf red;       // scal2 [2]
   DevBuf state;     // BicgState<T>
   DevBuf hist_d;
-  DevBuf fused_parts, fused_bar, fused_stats;  // single-kernel path
+  DevBuf fused_slots, fused_bar, fused_stats, fused_band;  // single-kernel path
+  int band_lo = -1, band_hi = -1;  // reach of the gathers below / above the diagonal (computed once, lazily)
 
   // Single-kernel solve: one GPU, Jacobi or no preconditioner, matrix + vectors resident in L2.
   bool fused_eligible(const CsrMat<T>* Am, PcMode pcm) const {
@@ -679,12 +943,12 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     // the whole solve in one cooperative kernel (see bicg_fused_kernel)
     // (y and z are always separate buffers here: they are what the other CTAs gather)
     FusedArgs<T> fa{bufptr<int>(Am->indptr), bufptr<int>(Am->cols), bufptr<T>(Am->vals), (int)n, rhs, x, r, r0, p, w0 + 3 * n, v, t, w0 + 6 * n,
-                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol, nullptr, 0, 0};
+                    dinv, st, nullptr, nullptr, hd, cap, max_iter, tol, nullptr, 0, 0, 0, 0, 0, 0, 0};
     if (const char* ps = getenv("SPB_FUSED_POLL_NS")) fa.poll_sleep = (unsigned)atoi(ps);
     const bool want_stats = getenv("SPB_FUSED_STATS") != nullptr;
     if (want_stats) {
-      fused_stats.ensure(sizeof(long long) * 16);
-      SPB_CUDA(cudaMemsetAsync(fused_stats.p, 0, sizeof(long long) * 16, c->stream));
+      fused_stats.ensure(sizeof(long long) * 10 * kFusedMaxGrid);
+      SPB_CUDA(cudaMemsetAsync(fused_stats.p, 0, sizeof(long long) * 10 * kFusedMaxGrid, c->stream));
       fa.stats = bufptr<long long>(fused_stats);
     }
     c->gate = nullptr;
@@ -698,12 +962,20 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     SPB_CUDA(cudaMemcpyAsync(&fin, st, sizeof(fin), cudaMemcpyDeviceToHost, c->stream));
     SPB_CUDA(cudaStreamSynchronize(c->stream));
     if (want_stats) {
-      long long hs[16];
-      SPB_CUDA(cudaMemcpy(hs, fused_stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
-      static const char* nm[10] = {"K1", "SpMV1", "K2", "SpMV2", "K3", "block partial", "reduction barrier", "partial sum", "plain barrier", "scalar step"};
+      std::vector<long long> hs(10 * kFusedMaxGrid);
+      SPB_CUDA(cudaMemcpy(hs.data(), fused_stats.p, sizeof(long long) * hs.size(), cudaMemcpyDeviceToHost));
+      static const char* nm[10] = {"K1", "SpMV1", "K2", "SpMV2", "K3", "block partial", "reduction wait", "partial sum", "gather hand-off", "scalar step"};
       const double its = (double)std::max<long long>(fin.h.its, 1);
-      fprintf(stderr, "[bicg_fused] clocks per iteration (CTA 0):");
-      for (int k = 0; k < 10; ++k) fprintf(stderr, " %s=%.0f", nm[k], (double)hs[k] / its);
+      int ng = 0;
+      for (int b = 0; b < kFusedMaxGrid; ++b)
+        if (hs[10 * b + 5] > 0) ng = b + 1;
+      fprintf(stderr, "[bicg_fused] clocks per iteration, min / median / max over %d CTAs:", ng);
+      for (int k = 0; k < 10; ++k) {
+        std::vector<double> v;
+        for (int b = 0; b < ng; ++b) v.push_back((double)hs[10 * b + k] / its);
+        std::sort(v.begin(), v.end());
+        if (!v.empty()) fprintf(stderr, " %s=%.0f/%.0f/%.0f", nm[k], v.front(), v[v.size() / 2], v.back());
+      }
       fprintf(stderr, "\n");
     }
     int rcf;
@@ -887,35 +1159,106 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
   const int block = be && *be ? atoi(be) : 512;
   const char* se = getenv("SPB_FUSED_SMEM");
   const bool allow_smem = !(se && *se == '0');
+  const char* we = getenv("SPB_FUSED_WIN");
+  const bool allow_win = allow_smem && !(we && *we == '0');
   int smem_cap = 0;
   SPB_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  auto run = [&](auto kern_sv, auto kern_gl, int BLOCK) {
-    // one CTA per SM (the shared-memory variant needs most of an SM's shared memory anyway)
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->sm_count, ceil_div(n, BLOCK)));
-    const int spt = (int)ceil_div(n, (int64_t)grid * BLOCK);
-    const size_t smem = ((size_t)5 * sizeof(T) + (PC ? sizeof(V) : 0) + sizeof(int2)) * (size_t)spt * BLOCK + 16;
-    const bool sv = allow_smem && smem + 4096 <= (size_t)smem_cap;
-    fa.slots_per_thread = spt;
-    fused_parts.ensure(sizeof(Acc<T>) * 6 * (size_t)grid);
+  if (allow_win && band_lo < 0) {  // bandwidth of the matrix: decides whether the gathered vector fits a shared-memory window
+    fused_band.ensure(sizeof(int) * 2);
+    SPB_CUDA(cudaMemsetAsync(fused_band.p, 0, sizeof(int) * 2, c->stream));
+    {
+      LaunchScope ls(c, FAM_SCALAR);
+      fused_band_kernel<<<(int)std::min<int64_t>(ceil_div(n, 256), 1024), 256, 0, c->stream>>>(fa.indptr, fa.cols, (int)n, bufptr<int>(fused_band));
+      check_launch("fused_band_kernel");
+    }
+    int hb[2] = {0, 0};
+    SPB_CUDA(cudaMemcpyAsync(hb, fused_band.p, sizeof(hb), cudaMemcpyDeviceToHost, c->stream));
+    SPB_CUDA(cudaStreamSynchronize(c->stream));
+    band_lo = hb[0];
+    band_hi = hb[1];
+  }
+  const char* ce = getenv("SPB_FUSED_CLUSTER");
+  const bool allow_cluster = allow_win && !(ce && *ce == '0');
+  auto run = [&](auto kern_cl, auto kern_sv, auto kern_gl, int BLOCK) {
+    constexpr int AW = (int)sizeof(Acc<T>) / 8;
+    const size_t per_slot = (size_t)6 * sizeof(T) + (PC ? sizeof(V) : 0) + sizeof(int2);
+    fa.bw_lo = std::max(band_lo, 0);
+    fa.bw_hi = std::max(band_hi, 0);
     fused_bar.ensure(sizeof(unsigned long long) * 2);
-    fa.parts = bufptr<Acc<T>>(fused_parts);
     fa.bar = bufptr<unsigned long long>(fused_bar);
     SPB_CUDA(cudaMemsetAsync(fused_bar.p, 0, sizeof(unsigned long long) * 2, c->stream));
+    // ---- MODE 2: the whole system inside one thread-block cluster (<= 4 rows per thread)
+    if (allow_cluster && band_lo >= 0) {
+      const int gc = (int)std::max<int64_t>(1, std::min<int64_t>(kFusedCluster, ceil_div(n, BLOCK)));
+      const int R = (int)ceil_div(n, (int64_t)gc);
+      const int spt = (int)ceil_div((int64_t)R, (int64_t)BLOCK);
+      const size_t smem_sv = (per_slot * (size_t)spt * BLOCK + 15) / 16 * 16;
+      const int64_t win_elems = (int64_t)R + fa.bw_lo + fa.bw_hi;
+      const size_t smem_win = (smem_sv + (size_t)win_elems * sizeof(T) + 31) / 16 * 16;
+      // matrix slice: mean entries per CTA + 25 % (a CTA whose slice is larger reads its matrix from global memory)
+      const int64_t nnz_all = static_cast<CsrMat<T>*>(A)->nnz;
+      int64_t mat_cap = (nnz_all / gc) + (nnz_all / gc) / 4 + 64;
+      size_t smem_all = smem_win + (size_t)mat_cap * (sizeof(int) + sizeof(T)) + 48;
+      if (smem_all + 4096 > (size_t)smem_cap) {
+        mat_cap = 0;
+        smem_all = smem_win + 48;
+      }
+      const bool force = ce && *ce == '1';
+      if ((spt <= 4 || force) && smem_all + 4096 <= (size_t)smem_cap) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(gc);
+        cfg.blockDim = dim3(BLOCK);
+        cfg.dynamicSmemBytes = smem_all;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = gc;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int nclusters = 0;
+        const bool ok = cudaFuncSetAttribute(kern_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_all) == cudaSuccess &&
+                        cudaFuncSetAttribute(kern_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaOccupancyMaxActiveClusters(&nclusters, kern_cl, &cfg) == cudaSuccess && nclusters >= 1;
+        if (ok) {
+          fa.slots_per_thread = spt;
+          fa.rows_per_cta = R;
+          fa.win_elems = (int)win_elems;
+          fa.mat_cap = (int)mat_cap;
+          LaunchScope ls(c, FAM_VEC);
+          SPB_CUDA(cudaLaunchKernelEx(&cfg, kern_cl, fa));
+          return;
+        }
+        cudaGetLastError();  // the cluster shape is not available on this device: use the grid modes
+      }
+    }
+    // ---- MODE 0 / 1: cooperative grid, one CTA per SM (the shared-memory variant needs most of an SM's shared memory anyway)
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(c->sm_count, kFusedMaxGrid), ceil_div(n, BLOCK)));
+    const int R = (int)ceil_div(n, (int64_t)grid);
+    const int spt = (int)ceil_div((int64_t)R, (int64_t)BLOCK);
+    const size_t smem_sv = (per_slot * (size_t)spt * BLOCK + 15) / 16 * 16 + 64;
+    const bool sv = allow_smem && smem_sv + 4096 <= (size_t)smem_cap;
+    fa.slots_per_thread = spt;
+    fa.rows_per_cta = R;
+    fa.win_elems = 0;
+    fa.mat_cap = 0;
+    fused_slots.ensure(sizeof(double) * 3 * 2 * AW * (size_t)grid);
+    fa.rslots = bufptr<double>(fused_slots);
     LaunchScope ls(c, FAM_VEC);
     void* args[] = {(void*)&fa};
     if (sv) {
-      SPB_CUDA(cudaFuncSetAttribute(kern_sv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern_sv, dim3(grid), dim3(BLOCK), args, smem, c->stream));
+      SPB_CUDA(cudaFuncSetAttribute(kern_sv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sv));
+      SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern_sv, dim3(grid), dim3(BLOCK), args, smem_sv, c->stream));
     } else {
       SPB_CUDA(cudaLaunchCooperativeKernel((void*)kern_gl, dim3(grid), dim3(BLOCK), args, 0, c->stream));
     }
   };
-  if (block >= 1024)
-    run(bicg_fused_kernel<T, V, PC, 1024, true>, bicg_fused_kernel<T, V, PC, 1024, false>, 1024);
-  else if (block >= 512)
-    run(bicg_fused_kernel<T, V, PC, 512, true>, bicg_fused_kernel<T, V, PC, 512, false>, 512);
+  if (block >= 512)
+    run(bicg_fused_kernel<T, V, PC, 512, 2>, bicg_fused_kernel<T, V, PC, 512, 1>, bicg_fused_kernel<T, V, PC, 512, 0>, 512);
   else
-    run(bicg_fused_kernel<T, V, PC, 256, true>, bicg_fused_kernel<T, V, PC, 256, false>, 256);
+    run(bicg_fused_kernel<T, V, PC, 256, 2>, bicg_fused_kernel<T, V, PC, 256, 1>, bicg_fused_kernel<T, V, PC, 256, 0>, 256);
 }
 
 spb_solver* make_bicgstab(spb_op* A, int64_t size) {

@@ -127,6 +127,15 @@ __device__ __forceinline__ bool wv_is_sentinel(double v) {
 __device__ __forceinline__ bool wv_is_sentinel(cplx v) { return wv_is_sentinel(v.re) || wv_is_sentinel(v.im); }
 __device__ __forceinline__ bool wv_is_sentinel(float v) { return (unsigned)__float_as_int(v) == SPB_GS_SENTINEL32; }
 __device__ __forceinline__ bool wv_is_sentinel(cplxf v) { return wv_is_sentinel(v.re) || wv_is_sentinel(v.im); }
+// A computed x that happens to BE the sentinel pattern (only possible when the caller's rhs carries a NaN with
+// exactly this payload: NaN payloads propagate through the arithmetic) is handed on as a different NaN, so a
+// consumer never mistakes it for "not there yet"; the output vector keeps the original bits.
+__device__ __forceinline__ double wv_handoff(double v) {
+  return wv_is_sentinel(v) ? __longlong_as_double((long long)(SPB_GS_SENTINEL ^ 1ULL)) : v;
+}
+__device__ __forceinline__ float wv_handoff(float v) { return wv_is_sentinel(v) ? __int_as_float((int)(SPB_GS_SENTINEL32 ^ 1u)) : v; }
+__device__ __forceinline__ cplx wv_handoff(cplx v) { return cplx{wv_handoff(v.re), wv_handoff(v.im)}; }
+__device__ __forceinline__ cplxf wv_handoff(cplxf v) { return cplxf{wv_handoff(v.re), wv_handoff(v.im)}; }
 __device__ __forceinline__ void wv_publish(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
@@ -388,10 +397,11 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
         if (!BWD && a.aux)
           for (int e = 0; e < Wo; ++e) sigma = add(sigma, auxs[e * nrows + i]);
         const T x = divi(sub(rv, sigma), dv);  // src/gauss_seidel.rs:123
-        xs[row - r0] = x;
+        const T xh = wv_handoff(x);
+        xs[row - r0] = xh;
         for (int e = 0; e < Wm; ++e) {  // deliver to the blocks that wait for this value
           const uint32_t m = mail[e * nrows + i];
-          if (m != SPB_WAVE_NOMAIL) wv_publish(a.mailbox + m, x);
+          if (m != SPB_WAVE_NOMAIL) wv_publish(a.mailbox + m, xh);
         }
         a.out[row] = x;
       }
