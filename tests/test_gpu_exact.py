@@ -130,6 +130,39 @@ def test_history_bit_for_bit_live(sp, exact, case, monkeypatch):
         _same(_gpu_solve(sp, A, rhs, solver, tol, max_iter, pc), o)
 
 
+FUSED_MODES = [  # (id, environment) -- csrc/bicgstab.cu: bicg_fused_kernel<.., BLOCK, MODE>
+    ("grid_global_256", {"SPB_FUSED_SMEM": "0", "SPB_FUSED_CLUSTER": "0", "SPB_FUSED_BLOCK": "256"}),
+    ("grid_global_512", {"SPB_FUSED_SMEM": "0", "SPB_FUSED_CLUSTER": "0", "SPB_FUSED_BLOCK": "512"}),
+    ("grid_smem_256", {"SPB_FUSED_CLUSTER": "0", "SPB_FUSED_BLOCK": "256"}),
+    ("grid_smem_512", {"SPB_FUSED_CLUSTER": "0", "SPB_FUSED_BLOCK": "512"}),
+    ("cluster_256", {"SPB_FUSED_CLUSTER": "1", "SPB_FUSED_BLOCK": "256"}),
+    ("cluster_512", {"SPB_FUSED_CLUSTER": "1", "SPB_FUSED_BLOCK": "512"}),
+]
+
+
+@pytest.mark.parametrize("mode", FUSED_MODES, ids=[m[0] for m in FUSED_MODES])
+def test_fused_kernel_modes_bit_for_bit(sp, exact, mode, monkeypatch):
+    """Every mode of the single-kernel BiCGStab -- cooperative grid with global or shared-memory vectors, and the
+    one-cluster mode (distributed shared memory, matrix slice + window in shared memory) -- reproduces the exact-dot
+    oracle in every bit: Jacobi on the reference Dirichlet matrix (several CTAs, 1-2 rows per thread), a 27-point
+    matrix whose window is wider than a CTA's rows, the rho-restart path across several CTAs, a complex system without
+    preconditioner, and a system of one partial CTA."""
+    monkeypatch.setenv("SPB_FUSED", "1")
+    for k, v in mode[1].items():
+        monkeypatch.setenv(k, v)
+    cases = [
+        (exact.gen_dirichlet2d(100), "diag", 1e-8, 2000),
+        (_ones_rhs(exact, exact.gen_convdiff27(14, 13, 12)), "diag", 1e-8, 500),
+        (_ones_rhs(exact, exact.gen_lap3d7(12, shift=0.0)), None, 1e-30, 300),  # rho restart, 1728 rows
+        (_ones_rhs(exact, exact.gen_lap3d7(11, 10, 9, shift=0.5 + 0.5j, dtype=np.complex128), 1 + 1j), None, 1e-8, 600),
+        (_ones_rhs(exact, exact.gen_lap3d7(5, 4, 3, shift=0.05)), "diag", 1e-10, 200),
+    ]
+    for (A, rhs), pck, tol, max_iter in cases:
+        pc = ("diag", A.diagonal()) if pck else None
+        o = exact.bicgstab(A, rhs, max_iter=max_iter, tol=tol, hist_cap=max_iter + 1, pc=pc)
+        _same(_gpu_solve(sp, A, rhs, "bicgstab", tol, max_iter, pc), o)
+
+
 def test_gauss_seidel_solver_bit_for_bit(sp, exact):
     """GaussSeidel::solve (src/gauss_seidel.rs:33-140): the sweeps are bit-exact and the per-sweep
     residual norm / the b-norm are exactly rounded on both sides."""
