@@ -76,7 +76,7 @@ __host__ __device__ inline int wave_a16(long long v) { return (int)((v + 15) & ~
 // header (32 B): nrows, nseg, W, nhalo, Wo, Wm, mailbox offset (lo, hi)
 #define SPB_WAVE_NOMAIL 0xFFFFFFFFu
 struct WaveLayout {
-  int seg_end, rowid, diag, eoff, eval, mail, hslot, total;
+  int seg_end, rowid, diag, eoff, eval, mail, hslot, hcol, total;
 };
 template <typename T>
 __host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, int nhalo, int Wm) {
@@ -96,6 +96,8 @@ __host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, in
   off += wave_a16(4LL * Wm * nrows);
   L.hslot = off;  // sentinel-filled landing slots of the cross-block values (mailbox order)
   off += wave_a16((long long)sizeof(T) * nhalo);
+  L.hcol = off;  // the column of every landing slot (cluster mode: which CTA's shared memory holds it)
+  off += wave_a16(4LL * nhalo);
   L.total = off;
   return L;
 }
@@ -174,14 +176,85 @@ __device__ __forceinline__ cplxf wv_lds<cplxf>(uint32_t addr) {
   asm volatile("ld.volatile.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.re), "=f"(v.im) : "r"(addr) : "memory");
   return v;
 }
+// ---- thread-block cluster: the x block of a neighbouring CTA of the same cluster is polled in ITS shared memory
+__device__ __forceinline__ uint32_t wv_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t wv_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void wv_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t wv_mapa(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  return ra;
+}
+__device__ __forceinline__ int wv_ld_remote_s32(uint32_t ra) {
+  int v;
+  asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ T wv_poll_remote(uint32_t ra);
+template <>
+__device__ __forceinline__ double wv_poll_remote<double>(uint32_t ra) {
+  double v;
+  asm volatile("ld.volatile.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+template <>
+__device__ __forceinline__ cplx wv_poll_remote<cplx>(uint32_t ra) {
+  cplx v;
+  asm volatile("ld.volatile.shared::cluster.v2.f64 {%0,%1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(ra) : "memory");
+  return v;
+}
+template <>
+__device__ __forceinline__ float wv_poll_remote<float>(uint32_t ra) {
+  float v;
+  asm volatile("ld.volatile.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+template <>
+__device__ __forceinline__ cplxf wv_poll_remote<cplxf>(uint32_t ra) {
+  cplxf v;
+  asm volatile("ld.volatile.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(v.re), "=f"(v.im) : "r"(ra) : "memory");
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ void wv_sts_volatile(T* p, T v) {
+  *reinterpret_cast<volatile T*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void wv_sts_volatile<cplx>(cplx* p, cplx v) {
+  asm volatile("st.volatile.shared.v2.f64 [%0], {%1,%2};" ::"r"(smem_u32(p)), "d"(v.re), "d"(v.im) : "memory");
+}
+template <>
+__device__ __forceinline__ void wv_sts_volatile<cplxf>(cplxf* p, cplxf v) {
+  asm volatile("st.volatile.shared.v2.f32 [%0], {%1,%2};" ::"r"(smem_u32(p)), "f"(v.re), "f"(v.im) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ T wave_sentinel_value() {
+  const unsigned long long w[2] = {wave_sentinel_fill<T>(), wave_sentinel_fill<T>()};
+  T v;
+  memcpy(&v, w, sizeof(T));
+  return v;
+}
+
 // x value at a resolved shared-memory address; spins while the slot still holds the sentinel
 // (a cross-block value the helper warps have not delivered yet).
 template <typename T>
-__device__ __forceinline__ T wv_x(uint32_t addr, int* flag, int* err, long long& spins) {
+__device__ __forceinline__ T wv_x(uint32_t addr, int* flag, int* err, long long& spins, unsigned spin_ns) {
   T x = wv_lds<T>(addr);
   if (wv_is_sentinel(x)) {
     long long n = 0;
     do {
+      if (spin_ns) __nanosleep(spin_ns);  // leave the SM's load / store path to the helper warps that deliver the value
       x = wv_lds<T>(addr);
     } while (wv_is_sentinel(x) && ++n < (1LL << 26));
     if (wv_is_sentinel(x)) {  // a legitimate value that equals the sentinel (a NaN), or a stalled producer: use it, report it
@@ -209,6 +282,7 @@ struct WaveArgs {
   const int* gate;
   int gate_value;
   int* err;  // Ctx::dev_err
+  unsigned spin_ns;  // back-off of a row thread that waits for a value of another block
 };
 
 // Pre-pass (fully parallel): sentinel-fill the mailbox, permute rhs into sweep order, reduce the other
@@ -249,10 +323,14 @@ __global__ void __launch_bounds__(kVecThreads) gs_wave_prep_kernel(int64_t mb8, 
   }
 }
 
-template <typename T, bool BWD>
+// CL: the grid is launched in thread-block clusters; block tickets are handed out per cluster (rank r of the cluster
+// with ticket c sweeps block c * size + r), so consecutive blocks are co-resident CTAs of one cluster and a value
+// produced by one of them is polled by the helpers directly in the producer's shared-memory x block (ld.shared::cluster,
+// ~200 clocks) instead of the global mailbox (an L2 round trip per poll: ~3.2 k clocks of lag per block boundary measured).
+template <typename T, bool BWD, bool CL>
 __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs<T> a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  if (a.gate && *a.gate != a.gate_value) return;
+  if (a.gate && *a.gate != a.gate_value) return;  // (uniform over the grid)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + WAVE_MAX_STAGES;
   int* s_ticket = reinterpret_cast<int*>(smem + 2 * WAVE_MAX_STAGES * sizeof(uint64_t));
@@ -261,8 +339,9 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x;
   const long long t_start = a.stats ? clock64() : 0;
+  const uint32_t crank = CL ? wv_cluster_rank() : 0u, csize = CL ? wv_cluster_size() : 1u;
   if (tid == 0) {
-    *s_ticket = atomicAdd(a.ticket, 1);
+    if (crank == 0) *s_ticket = atomicAdd(a.ticket, 1);
     *reinterpret_cast<T*>(smem + WAVE_ZERO_OFF) = zero_of<T>();
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -270,8 +349,19 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  const int t = *s_ticket;  // blocks are processed in ticket order: a block waits only for earlier tickets
+  if (CL) {  // the x block starts as "nothing produced yet": its neighbours in the cluster poll it
+    const T sv = wave_sentinel_value<T>();
+    for (int i = tid; i < a.block_rows; i += WAVE_THREADS) xs[i] = sv;
+    wv_cluster_sync();
+  } else {
+    __syncthreads();
+  }
+  // blocks are processed in ticket order: a block waits only for earlier tickets
+  const int t = CL ? wv_ld_remote_s32(wv_mapa(smem_u32(s_ticket), 0)) * (int)csize + (int)crank : *s_ticket;
+  if (CL && t >= a.nblocks) {  // padding CTA of the last cluster
+    wv_cluster_sync();
+    return;
+  }
   const int b = BWD ? a.nblocks - 1 - t : t;
   const int r0 = b * a.block_rows;
   const int c0 = a.blk_chunk[t], c1 = a.blk_chunk[t + 1];
@@ -299,6 +389,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
   }
 
   if (tid >= WAVE_NC) {  // ---- helper warps: deliver the cross-block values of each chunk into its slots
+    // (all four warps work on the same chunk: one warp per chunk, the warps taking the chunks round robin, was measured
+    //  40 % slower -- 32 lanes with 8 polls each deliver a chunk later than 128 threads with 2)
     const int htid = tid - WAVE_NC;
     for (int c = c0; c < c1; ++c) {
       const int k = c - c0, s = k % S, u = k / S;
@@ -309,14 +401,31 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
       if (nhalo > 0) {
         const WaveLayout L = wave_layout<T>(hdr[0], hdr[1], hdr[2], nhalo, hdr[5]);
         T* hslot = reinterpret_cast<T*>(st + L.hslot);
+        const int* hcol = reinterpret_cast<const int*>(st + L.hcol);
         const T* mbox = a.mailbox + (((long long)hdr[7] << 32) | (unsigned)hdr[6]);  // this chunk's slots: contiguous
+        // where slot h is polled: the producer's shared-memory x block when it runs in this cluster, else the mailbox
+        auto poll = [&](int h, uint32_t ra) -> T { return (CL && ra) ? wv_poll_remote<T>(ra) : wv_poll(mbox + h); };
+        auto remote_of = [&](int h) -> uint32_t {
+          if (!CL) return 0u;
+          const int j = hcol[h];
+          const int pb = j / a.block_rows;
+          const int tp = BWD ? a.nblocks - 1 - pb : pb;
+          if (tp / (int)csize != t / (int)csize) return 0u;
+          return wv_mapa(smem_u32(xs + (j - pb * a.block_rows)), (uint32_t)(tp % (int)csize));
+        };
         // slots are sorted by need; thread t polls slots t, t + NH, ...: coalesced, and every thread starts early
         for (int h0 = htid; h0 < nhalo; h0 += WAVE_NH * WAVE_HB) {
           unsigned pend = 0;
           T v[WAVE_HB];
+          uint32_t ra[WAVE_HB];
 #pragma unroll
-          for (int j = 0; j < WAVE_HB; ++j)
-            if (h0 + j * WAVE_NH < nhalo) v[j] = wv_poll(mbox + h0 + j * WAVE_NH);
+          for (int j = 0; j < WAVE_HB; ++j) {
+            ra[j] = 0u;
+            if (h0 + j * WAVE_NH < nhalo) {
+              ra[j] = remote_of(h0 + j * WAVE_NH);
+              v[j] = poll(h0 + j * WAVE_NH, ra[j]);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < WAVE_HB; ++j) {
             if (h0 + j * WAVE_NH < nhalo) {
@@ -331,7 +440,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
 #pragma unroll
             for (int j = 0; j < WAVE_HB; ++j) {
               if (pend & (1u << j)) {
-                const T w = wv_poll(mbox + h0 + j * WAVE_NH);
+                const T w = poll(h0 + j * WAVE_NH, ra[j]);
                 if (!wv_is_sentinel(w)) {
                   hslot[h0 + j * WAVE_NH] = w;
                   pend &= ~(1u << j);
@@ -384,10 +493,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
           const T v2 = eval[(e + 2) * nrows + i], v3 = eval[(e + 3) * nrows + i];
           T x0 = wv_lds<T>(sbase + o0), x1 = wv_lds<T>(sbase + o1), x2 = wv_lds<T>(sbase + o2), x3 = wv_lds<T>(sbase + o3);
           if (wv_is_sentinel(x0) | wv_is_sentinel(x1) | wv_is_sentinel(x2) | wv_is_sentinel(x3)) {  // rare: wait for a neighbour block
-            x0 = wv_x<T>(sbase + o0, a.ticket + 1, a.err, spins);
-            x1 = wv_x<T>(sbase + o1, a.ticket + 1, a.err, spins);
-            x2 = wv_x<T>(sbase + o2, a.ticket + 1, a.err, spins);
-            x3 = wv_x<T>(sbase + o3, a.ticket + 1, a.err, spins);
+            x0 = wv_x<T>(sbase + o0, a.ticket + 1, a.err, spins, a.spin_ns);
+            x1 = wv_x<T>(sbase + o1, a.ticket + 1, a.err, spins, a.spin_ns);
+            x2 = wv_x<T>(sbase + o2, a.ticket + 1, a.err, spins, a.spin_ns);
+            x3 = wv_x<T>(sbase + o3, a.ticket + 1, a.err, spins, a.spin_ns);
           }
           sigma = add(sigma, mul(v0, x0));
           sigma = add(sigma, mul(v1, x1));
@@ -398,7 +507,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
           for (int e = 0; e < Wo; ++e) sigma = add(sigma, auxs[e * nrows + i]);
         const T x = divi(sub(rv, sigma), dv);  // src/gauss_seidel.rs:123
         const T xh = wv_handoff(x);
-        xs[row - r0] = xh;
+        if (CL)
+          wv_sts_volatile(xs + (row - r0), xh);  // polled by the next blocks of the cluster
+        else
+          xs[row - r0] = xh;
         for (int e = 0; e < Wm; ++e) {  // deliver to the blocks that wait for this value
           const uint32_t m = mail[e * nrows + i];
           if (m != SPB_WAVE_NOMAIL) wv_publish(a.mailbox + m, xh);
@@ -421,6 +533,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
       a.stats[4 * t + 3] = bar_clk;
     }
   }
+  if (CL) wv_cluster_sync();  // the x block stays addressable until every block of the cluster is done (row warps only:
+                              // the producer / helper warps have exited or will, and exited threads are not waited for)
 }
 
 // ---- analysis ----------------------------------------------------------------------------------
@@ -820,6 +934,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
       put_bytes(stat, base + L.eval, ev.data(), ev.size());
       put_bytes(stat, base + L.mail, mail.data(), mail.size());
       put_bytes(stat, base + L.hslot, hs.data(), hs.size());
+      put_bytes(stat, base + L.hcol, plan_halo.data() + pl.hal_beg, nhalo);
       chunks[ci] = d;
     }
   };
@@ -888,10 +1003,12 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   const int rhs_bytes = wave_a16((long long)sizeof(T) * ws.stage_rows);
   const int oth_bytes = wave_a16((long long)sizeof(T) * ws.stage_other);
   const int stage_bytes = (ws.stage_static + rhs_bytes + oth_bytes + 127) / 128 * 128;
-  if (M->A->ip64)
-    wave_prep_launch<T, int64_t>(M, ws, rhs, other);
-  else
-    wave_prep_launch<T, int32_t>(M, ws, rhs, other);
+  auto prep = [&]() {
+    if (M->A->ip64)
+      wave_prep_launch<T, int64_t>(M, ws, rhs, other);
+    else
+      wave_prep_launch<T, int32_t>(M, ws, rhs, other);
+  };
   WaveArgs<T> a{};
   a.stat = bufptr<unsigned char>(ws.stat);
   a.chunks = bufptr<WaveChunk>(ws.chunks);
@@ -911,12 +1028,89 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   a.gate = c->gate;
   a.gate_value = c->gate_value;
   a.err = c->dev_err;
-  auto kern = ws.backward ? gs_wave_kernel<T, true> : gs_wave_kernel<T, false>;
-  // per launch, not cached: the attribute is per device and a process may hold contexts on several
-  SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem_bytes));
-  LaunchScope lsc(c, FAM_PRECOND);
-  kern<<<ws.nblocks, WAVE_THREADS, ws.smem_bytes, c->stream>>>(a);
-  check_launch("gs_wave_kernel");
+  {
+    const char* se = getenv("SPB_GS_SPIN_NS");
+    a.spin_ns = se && *se ? (unsigned)atoi(se) : 0u;
+  }
+  // One sweep = the pre-pass + the wavefront kernel.  want > 0: cluster launch (consecutive blocks = CTAs of one cluster,
+  // hand-offs through distributed shared memory) with `want` CTAs per cluster (16 = non-portable size) or the next
+  // smaller size the device can co-schedule with this footprint; 0: plain CTAs + mailbox.  Returns the size used.
+  auto run = [&](int want) -> int {
+    prep();
+    LaunchScope lsc(c, FAM_PRECOND);
+    int csize = ws.nblocks < 2 ? 0 : want;
+    while (csize >= 2) {
+      auto kc = ws.backward ? gs_wave_kernel<T, true, true> : gs_wave_kernel<T, false, true>;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(ceil_div((int64_t)ws.nblocks, (int64_t)csize) * csize));
+      cfg.blockDim = dim3(WAVE_THREADS);
+      cfg.dynamicSmemBytes = ws.smem_bytes;
+      cfg.stream = c->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = (unsigned)csize;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      const bool ok = cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem_bytes) == cudaSuccess &&
+                      (csize <= 8 || cudaFuncSetAttribute(kc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) &&
+                      cudaOccupancyMaxActiveClusters(&ncl, kc, &cfg) == cudaSuccess && ncl >= 1;
+      if (ok) {
+        SPB_CUDA(cudaLaunchKernelEx(&cfg, kc, a));
+        check_launch("gs_wave_kernel (cluster)");
+        return csize;
+      }
+      cudaGetLastError();
+      csize /= 2;
+    }
+    auto kern = ws.backward ? gs_wave_kernel<T, true, false> : gs_wave_kernel<T, false, false>;
+    // per launch, not cached: the attribute is per device and a process may hold contexts on several
+    SPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem_bytes));
+    kern<<<ws.nblocks, WAVE_THREADS, ws.smem_bytes, c->stream>>>(a);
+    check_launch("gs_wave_kernel");
+    return 0;
+  };
+  if (ws.cluster < 0) {
+    // First sweep of this schedule: which launch shape is fastest depends on how the blocks map onto the GPCs
+    // (measured on B200: 7-point 100^3, 100 blocks: clusters of 16 are 13 % faster; 128^3, 128 blocks: 2-5 % slower).
+    // A sweep is a pure function of its inputs (the pre-pass resets mailbox and ticket), so it is simply run with each
+    // candidate and timed -- same bits whatever is chosen.  SPB_GS_CLUSTER fixes the choice.
+    const char* ce = getenv("SPB_GS_CLUSTER");
+    if (ce && *ce) {
+      ws.cluster = std::max(0, atoi(ce));
+    } else if (c->gate || ws.nblocks < 4) {
+      ws.cluster = 0;  // (inside a gated launch queue the kernels may be no-ops: nothing to time)
+    } else {
+      cudaEvent_t e0, e1;
+      SPB_CUDA(cudaEventCreate(&e0));
+      SPB_CUDA(cudaEventCreate(&e1));
+      float best_ms = 0.f;
+      int best = 0, last_used = -1;
+      for (int cand : {16, 8, 0}) {
+        const int used = run(cand);  // warm-up, and what the device really grants
+        if (used == last_used) continue;
+        last_used = used;
+        SPB_CUDA(cudaEventRecord(e0, c->stream));
+        run(used);
+        run(used);
+        SPB_CUDA(cudaEventRecord(e1, c->stream));
+        SPB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        SPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (best_ms == 0.f || ms < best_ms) {
+          best_ms = ms;
+          best = used;
+        }
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      ws.cluster = best;
+    }
+  }
+  run(ws.cluster);
 }
 
 #define SPB_INST_WAVE(T)                                                                                              \

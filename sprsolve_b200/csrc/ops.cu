@@ -332,6 +332,21 @@ GsOp<T>* gs_create(CsrMat<T>* A, int mode, double omega) {
         op->wave_stats.alloc(sizeof(long long) * 4 * (size_t)op->wfwd.nblocks);
         SPB_CUDA(cudaMemset(op->wave_stats.p, 0, op->wave_stats.bytes));
       }
+      // launch shape of the sweeps (thread-block clusters of 16 / 8 CTAs or plain CTAs): timed once, here, on scratch
+      // vectors -- inside a solver the launch queue is gated and nothing could be timed (csrc/gs_wave.cu: wave_sweep)
+      if ((op->wfwd.ok || op->wbwd.ok) && n > 0) {
+        DevBuf tr, to, tx;
+        tr.alloc(sizeof(T) * (size_t)n);
+        to.alloc(sizeof(T) * (size_t)n);
+        tx.alloc(sizeof(T) * (size_t)n);
+        SPB_CUDA(cudaMemsetAsync(tr.p, 0, tr.bytes, c->stream));
+        SPB_CUDA(cudaMemsetAsync(to.p, 0, to.bytes, c->stream));
+        if (op->wfwd.ok) wave_sweep<T>(op, op->wfwd, bufptr<T>(tr), bufptr<T>(to), bufptr<T>(tx));
+        if (op->wbwd.ok) wave_sweep<T>(op, op->wbwd, bufptr<T>(tr), bufptr<T>(to), bufptr<T>(tx));
+        SPB_CUDA(cudaStreamSynchronize(c->stream));
+        if (getenv("SPB_GS_TIMING"))
+          fprintf(stderr, "[gs_wave] launch shape: forward cluster %d, backward cluster %d (0 = plain CTAs)\n", op->wfwd.cluster, op->wbwd.cluster);
+      }
     }
     // The global level schedule (cooperative grid-barrier kernel) is only the fallback: built now
     // when a wavefront schedule is unavailable, otherwise on first use (ensure_levels).

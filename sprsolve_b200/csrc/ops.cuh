@@ -58,6 +58,7 @@ struct WaveSched {
   DevBuf mailbox;    // T [mailbox_slots]: cross-block values, one contiguous slot range per consumer chunk (per apply)
   int64_t mailbox_slots = 0;
   DevBuf ticket;     // int32 [4]: block ticket, timeout flag
+  int cluster = -1;  // CTAs per thread-block cluster of the sweep launch (0: none; -1: decided by the first sweep)
 };
 
 template <typename T>
