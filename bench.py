@@ -26,7 +26,8 @@ roofline: the SpMV kernel (dominant: ~80 % of an iteration's bytes).  `achieved`
           duration measured live with CUDA events around every SpMV launch of one extra profiled
           step.  Plain CSR: nnz*12 + (n+1)*sizeof(indptr) + 2*n*8.  When the
           analysis finds the column-offset dictionary (27-point matrix: 27 row patterns) the column
-          stream does not exist: nnz*8 + n*2 (pattern ids) + (n+1)*sizeof(indptr) + 2*n*8 -- these
+          stream and the row-pointer stream do not exist: nnz*8 + (n+1)*4 (row words: pattern id + low 16
+          bits of the row pointer) + 2*n*8 -- these
           are the bytes the HBM roofline bounds, so `frac` = achieved/peak stays a physical fraction.
           `csr_equivalent_*` quote the same launch in the reference operator's CSR bytes (can exceed
           the peak: a speed-up in format, not in bandwidth).
@@ -433,7 +434,7 @@ def run_gpu(args):
     avg_ms = max_over_ranks(ms_spmv / n_products)
     # What the analysis chose for this matrix.  `achieved` counts the algorithmic bytes of the operand
     # format the kernel consumes: with the column-offset dictionary there is no column
-    # stream (8 + 2/row instead of 12 bytes per non-zero), which is what the HBM roofline bounds.
+    # stream (8 bytes per non-zero + 4 per row instead of 12 + 4..8 per row), which is what the HBM roofline bounds.
     # The same launch in the reference operator's CSR bytes is `csr_equivalent_*`.
     plan = A.plan_info()
     stream = plan["stream_bytes"]
@@ -454,7 +455,7 @@ def run_gpu(args):
         "bound": "hbm", "kernel": "spmv_tma_kernel<double> (CSR SpMV, 27-pt, this rank's rows)", "achieved": achieved, "peak": peak,
         "unit": "GB/s (per GPU)", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "frac_basis": "algorithmic bytes of the operand format the kernel consumes (bytes_per_launch)",
-        "format": (f"CSR values + 16-bit row-pattern ids ({plan['patterns']} column-offset patterns found by the analysis)"
+        "format": (f"CSR values + one 32-bit row word (16-bit pattern id + low 16 bits of the row pointer; {plan['patterns']} column-offset patterns found by the analysis)"
                    if plan["dictionary"] else "CSR values + int32 column indices"),
         "csr_equivalent_bytes_per_launch": b_spmv, "csr_equivalent_gbs": csr_eq, "csr_equivalent_frac": csr_eq / peak,
         "plan": {k: plan[k] for k in ("consumer_threads", "stages", "tile_nnz", "ctas_per_sm")},

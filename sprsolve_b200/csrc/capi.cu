@@ -396,9 +396,10 @@ template <typename T>
 void csr_plan_info_impl(spb_op* op, int64_t* info) {
   auto* m = static_cast<CsrMat<T>*>(op);
   const int64_t ipb = m->ip64 ? 8 : 4, vb = (int64_t)sizeof(T);
-  // bytes one mul_vec streams from HBM by design: values (+ column indices unless the pattern
-  // dictionary replaces them by a 16-bit id per row) + row pointers + x once + y once
-  const int64_t stream = m->nnz * (vb + (m->dict_on ? 0 : 4)) + (m->n_local + 1) * ipb + (m->dict_on ? 2 * m->n_local : 0) + 2 * m->n_local * vb;
+  // bytes one mul_vec streams from HBM by design: values + x once + y once + either column indices and row pointers
+  // (plain CSR) or one 32-bit word per row (dictionary: 16-bit pattern id + the low 16 bits of the row pointer)
+  const int64_t stream = m->dict_on ? m->nnz * vb + 4 * (m->n_local + 1) + 2 * m->n_local * vb
+                                    : m->nnz * (vb + 4) + (m->n_local + 1) * ipb + 2 * m->n_local * vb;
   // (info[0]: 0 plain CSR stream, 1 dictionary, 3 dictionary + x window in shared memory)
   const int64_t v[8] = {(m->dict_on ? 1 : 0) | (m->dict_on && m->xwin_on ? 2 : 0), m->dict_u, m->dict_w, m->plan_ct, m->plan_stages, m->plan_tile, m->plan_bps, stream};
   for (int i = 0; i < 8; ++i) info[i] = v[i];

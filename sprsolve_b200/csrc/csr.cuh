@@ -62,7 +62,7 @@ struct CsrMat : spb_op {
   int dict_w = 0;        // dictionary row stride = longest row
   int64_t dict_u = 0;    // number of distinct row patterns
   DevBuf dict_off;       // int32 [dict_u * dict_w]: col - row of the pattern's entries
-  DevBuf pid;            // uint16 [n_local]: pattern id of every row
+  DevBuf pid;            // uint32 [n_local + 1]: pattern id | (low 16 bits of indptr[row]) << 16 (the DICT kernels' row words)
   // --- x window (spmv.cu): the distinct column offsets of a stencil-like matrix form a few runs of
   //     consecutive values; per tile the x entries of every run are ONE contiguous segment, staged in
   //     shared memory with a bulk copy, and the gathers become shared-memory reads

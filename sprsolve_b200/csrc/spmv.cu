@@ -87,7 +87,7 @@ struct SpmvArgs {
   long long halo_stride;
   long long first_boundary;
   // column-offset dictionary (DICT kernels): row r has columns r + doff[pid[r] * dict_w + k]
-  const unsigned short* pid;
+  const unsigned* rinfo;  // DICT: per row (pattern id) | (low 16 bits of indptr[row]) << 16, n + 1 entries
   const int* doff;
   int dict_w;
   int* err;  // Ctx::dev_err: set when a neighbour's halo flag never arrived
@@ -175,6 +175,24 @@ __device__ __forceinline__ void row_range(const SpmvArgs<T, IP>& a, const TileMe
   }
 }
 
+// DICT kernels: extent and pattern of row r from the staged row words -- the low 16 bits of the row pointers are enough
+// inside a tile (a stage holds < 65536 entries), so the 4- or 8-byte indptr stream is not read at all.
+template <typename T, typename IP>
+__device__ __forceinline__ void dict_row(const SpmvArgs<T, IP>& a, const TileMeta& m, const unsigned* s_info, int r, int& p0, int& p1,
+                                         int& pidv) {
+  if (m.pid_off >= 0) {
+    const unsigned i0 = s_info[m.pid_off + (r - m.r0)], i1 = s_info[m.pid_off + (r - m.r0) + 1];
+    const unsigned base = (unsigned)m.s4 & 0xFFFFu;
+    p0 = (int)(((i0 >> 16) - base) & 0xFFFFu);
+    p1 = (int)(((i1 >> 16) - base) & 0xFFFFu);
+    pidv = (int)(i0 & 0xFFFFu);
+  } else {  // a tile with more rows than the staging capacity: global memory
+    p0 = (int)((long long)a.indptr[r] - m.s4);
+    p1 = (int)((long long)a.indptr[r + 1] - m.s4);
+    pidv = (int)(a.rinfo[r] & 0xFFFFu);
+  }
+}
+
 // blockDim.x = CT consumer threads + one producer warp.
 template <typename T, typename IP, bool HALO, int EPI, bool CONJ_IN, bool DICT>
 __global__ void __launch_bounds__(288)
@@ -183,9 +201,9 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
   const int CT = (int)blockDim.x - 32;
   const int VAL_BYTES = align16i((a.tile + 4) * (int)sizeof(T));
   const int COL_BYTES = DICT ? 0 : align16i((a.tile + 4) * 4);  // DICT: the column stream is not read at all
-  const int IP_BYTES = align16i((a.rcap + 8) * (int)sizeof(IP));
+  const int IP_BYTES = DICT ? 0 : align16i((a.rcap + 8) * (int)sizeof(IP));  // DICT: row extents come with the pattern word
   const int XW_BYTES = DICT ? align16i(a.xw_elems * (int)sizeof(T)) : 0;
-  const int PID_BYTES = DICT ? align16i((a.rcap + 16) * 2) : 0;  // the tile's pattern ids (a dependent DRAM load otherwise)
+  const int PID_BYTES = DICT ? align16i((a.rcap + 16) * 4) : 0;  // the tile's row words: pattern id + low 16 bits of the row pointer
   const int STAGE_BYTES = VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES + PID_BYTES;  // vals | cols | indptr slice | x window | pattern ids
   const int STAGES = a.stages;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
@@ -253,7 +271,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           m.total = (int)(en - s4);
           const int ra = r0 & ~(IPV - 1);  // 16-byte aligned start of the indptr slice
           const int nip = ((r1 + 1 - ra) + IPV - 1) & ~(IPV - 1);
-          const bool ip_ok = nip <= a.rcap + 8 - IPV;
+          const bool ip_ok = !DICT && nip <= a.rcap + 8 - IPV;
           m.ip_off = ip_ok ? (r0 - ra) : -1;
           const uint32_t groups = (uint32_t)((m.total + 3) >> 2);
           // x window: every segment must lie inside the owned part of x (tiles at the ends of the row
@@ -270,14 +288,14 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
             }
           }
           m.win = win ? 1 : 0;
-          // pattern ids of the tile's rows: 8 ids per 16 bytes
-          const int pa = r0 & ~7;
-          const int npid = ((r1 - pa) + 7) & ~7;
-          const bool pid_ok = DICT && groups > 0 && npid <= a.rcap + 8;
+          // row words of the tile's rows r0 .. r1 (one more than rows: the end of the last row): 4 per 16 bytes
+          const int pa = r0 & ~3;
+          const int npid = ((r1 + 1 - pa) + 3) & ~3;
+          const bool pid_ok = DICT && groups > 0 && npid <= a.rcap + 12;
           m.pid_off = pid_ok ? (r0 - pa) : -1;
           meta[s] = m;
           const uint32_t bytes = groups * ((DICT ? 0u : 16u) + 4u * (uint32_t)sizeof(T)) + (ip_ok ? (uint32_t)nip * (uint32_t)sizeof(IP) : 0u) +
-                                 (win ? xw_bytes : 0u) + (pid_ok ? (uint32_t)npid * 2u : 0u);
+                                 (win ? xw_bytes : 0u) + (pid_ok ? (uint32_t)npid * 4u : 0u);
           if (bytes) {
             mbar_arrive_expect_tx(&full[s], bytes);
             if (groups) {
@@ -285,7 +303,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               if (!DICT) bulk_g2s(stage + VAL_BYTES, a.cols + s4, groups * 16u, &full[s], pol_stream);
             }
             if (ip_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES, a.indptr + ra, (uint32_t)nip * (uint32_t)sizeof(IP), &full[s], pol_stream);
-            if (pid_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES, a.pid + pa, (uint32_t)npid * 2u, &full[s], pol_stream);
+            if (pid_ok) bulk_g2s(stage + VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES, a.rinfo + pa, (uint32_t)npid * 4u, &full[s], pol_stream);
             if (win) {
               unsigned char* xw = stage + VAL_BYTES + COL_BYTES + IP_BYTES;
               for (int g = 0; g < a.xw_nseg; ++g) {
@@ -323,19 +341,18 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
       const T* s_val = reinterpret_cast<const T*>(stage);
       const int* s_col = reinterpret_cast<const int*>(stage + VAL_BYTES);
       const IP* s_ip = reinterpret_cast<const IP*>(stage + VAL_BYTES + COL_BYTES);
-      const unsigned short* s_pid = reinterpret_cast<const unsigned short*>(stage + VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES);
+      const unsigned* s_info = reinterpret_cast<const unsigned*>(stage + VAL_BYTES + COL_BYTES + IP_BYTES + XW_BYTES);
       if (DICT && m.total >= 0 && m.win) {
         // x window: every operand of the tile is in shared memory -- values from the stream, x from the
         // staged segments; the same sequential fold in CSR order, no global load on the critical path
         const T* s_xw = reinterpret_cast<const T*>(stage + VAL_BYTES + COL_BYTES + IP_BYTES);
         for (int r = m.r0 + tid; r < m.r1; r += CT) {
-          int p0, p1;
-          row_range(a, m, s_ip, r, p0, p1);
+          int p0, p1, pidv;
+          dict_row(a, m, s_info, r, p0, p1, pidv);
           T acc = zero_of<T>();
           T wv = zero_of<T>();
           if (EPI != EPI_NONE) wv = a.w[r];
           const int lr = r - m.r0;
-          const int pidv = m.pid_off >= 0 ? (int)s_pid[m.pid_off + lr] : (int)a.pid[r];
           const int4* dp = reinterpret_cast<const int4*>(a.soff + pidv * a.dict_w);
           int k = p0;
           for (; k + 8 <= p1; k += 8) {
@@ -367,8 +384,11 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
         const T* xh_adj = HALO ? (xh - a.n_local) : a.x;
         const int nl = a.n_local;
         for (int r = m.r0 + tid; r < m.r1; r += CT) {
-          int p0, p1;
-          row_range(a, m, s_ip, r, p0, p1);
+          int p0, p1, pidv = 0;
+          if (DICT)
+            dict_row(a, m, s_info, r, p0, p1, pidv);
+          else
+            row_range(a, m, s_ip, r, p0, p1);
           T acc = zero_of<T>();
           T wv = zero_of<T>();
           if (EPI != EPI_NONE) wv = a.w[r];  // early: hidden behind the fold
@@ -378,10 +398,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           // (dict_w is a multiple of 8 and padded with zero offsets: two 16-byte loads per batch,
           // also for the partial batch at the end of a row -- a padding entry gathers x[r])
           const int4* dp = nullptr;
-          if (DICT) {
-            const int pidv = m.pid_off >= 0 ? (int)s_pid[m.pid_off + (r - m.r0)] : (int)a.pid[r];
-            dp = reinterpret_cast<const int4*>(a.doff + pidv * a.dict_w);
-          }
+          if (DICT) dp = reinterpret_cast<const int4*>(a.doff + pidv * a.dict_w);
           for (; k + 8 <= p1; k += 8) {
             int c[8];
             T xv[8];
@@ -558,6 +575,13 @@ __global__ void dict_verify_kernel(const IP* indptr, const int* cols, int64_t n,
   }
 }
 
+// row word of the DICT kernels: pattern id | (low 16 bits of indptr[row]) << 16; entry n carries the end of the last row
+template <typename IP>
+__global__ void dict_pack_kernel(const IP* indptr, const unsigned short* pid, int64_t n, unsigned* rinfo) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= n; r += (int64_t)gridDim.x * blockDim.x)
+    rinfo[r] = (r < n ? (unsigned)pid[r] : 0u) | (((unsigned)indptr[r] & 0xFFFFu) << 16);
+}
+
 template <typename T, typename IP>
 static void build_dict_impl(CsrMat<T>* m) {
   Ctx* c = m->ctx;
@@ -656,8 +680,17 @@ static void build_dict_impl(CsrMat<T>* m) {
     if (!(e && *e == '1') && !pays_without_window && !window_possible) return;  // keep the plain column stream
     m->xwin_on = window_possible;  // (the layout is fixed by build_plan, which may still drop it)
   }
+  DevBuf rinfo;
+  rinfo.alloc(sizeof(unsigned) * ((size_t)n + 1 + 16));
+  SPB_CUDA(cudaMemsetAsync(rinfo.p, 0, rinfo.bytes, c->stream));
+  {
+    LaunchScope ls(c, FAM_SCALAR);
+    dict_pack_kernel<IP><<<grid, 256, 0, c->stream>>>(ip, pid.as<unsigned short>(), n, rinfo.as<unsigned>());
+    check_launch("dict_pack_kernel");
+  }
+  SPB_CUDA(cudaStreamSynchronize(c->stream));  // (pid goes out of scope)
   m->dict_off = std::move(doff);
-  m->pid = std::move(pid);
+  m->pid = std::move(rinfo);
   m->dict_w = w;
   m->dict_u = u;
   m->dict_on = true;
@@ -667,9 +700,9 @@ static void build_dict_impl(CsrMat<T>* m) {
 template <typename T, typename IP>
 static size_t spmv_smem_bytes(const CsrMat<T>* m) {
   const size_t stage = (size_t)align16i((m->plan_tile + 4) * (int)sizeof(T)) + (m->dict_on ? 0 : align16i((m->plan_tile + 4) * 4)) +
-                       align16i((m->plan_rcap + 8) * (int)sizeof(IP));
+                       (m->dict_on ? 0 : align16i((m->plan_rcap + 8) * (int)sizeof(IP)));
   const size_t xw = m->dict_on && m->xwin_on ? (size_t)align16i(m->xwin_elems * (int)sizeof(T)) : 0;
-  const size_t pidb = m->dict_on ? (size_t)align16i((m->plan_rcap + 16) * 2) : 0;
+  const size_t pidb = m->dict_on ? (size_t)align16i((m->plan_rcap + 16) * 4) : 0;
   return m->plan_stages * (stage + xw + pidb) + kMaxStages * (16 + sizeof(TileMeta)) + 32 * sizeof(Acc<T>) + 32;
 }
 
@@ -986,7 +1019,7 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
                              list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
-                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
+                             bufptr<unsigned>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
       set_window(a);
       launch_spmv<T, int64_t>(this, a, epi_mode, conj_in, grid);
     } else {
@@ -994,7 +1027,7 @@ void CsrMat<T>::mul(const T* x, T* y, int epi_mode, const T* w, bool conj_in) {
                              list, nt, x, halo_ptr, (int)n_local, y, w,
                              bufptr<Acc<T>>(partials) + 2 * part_off, c->gate, c->gate_value,
                              plan_tile, plan_rcap, plan_stages, hhead, hstride, first_boundary,
-                             bufptr<unsigned short>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
+                             bufptr<unsigned>(pid), bufptr<int>(dict_off), dict_w, c->dev_err};
       set_window(a);
       launch_spmv<T, int32_t>(this, a, epi_mode, conj_in, grid);
     }
