@@ -439,7 +439,20 @@ __device__ __forceinline__ void fused_spmv_win(const FusedArgs<T>& a, const int2
     const int2 e = ext[l];
     T acc = zero_of<T>();
     if (mat_smem) {
-      for (int k = e.x - mbase; k < e.y - mbase; ++k) acc = add(acc, mul(win[mcols[k]], mvals[k]));
+      // 8 entries per batch: the column -> x loads of a batch are independent, only the fold is a chain
+      for (int k = e.x - mbase; k < e.y - mbase; k += 8) {
+        const int k1 = e.y - mbase;
+        T xv[8], m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int kk = min(k + j, k1 - 1);
+          xv[j] = win[mcols[kk]];
+          m[j] = mvals[kk];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (k + j < k1) acc = add(acc, mul(xv[j], m[j]));
+      }
     } else {
       for (int k = e.x; k < e.y; k += 8) {
         int c[8];
