@@ -30,7 +30,8 @@ roofline: the SpMV kernel (dominant: ~80 % of an iteration's bytes).  `achieved`
           bits of the row pointer) + 2*n*8 -- these
           are the bytes the HBM roofline bounds, so `frac` = achieved/peak stays a physical fraction.
           `csr_equivalent_*` quote the same launch in the reference operator's CSR bytes (can exceed
-          the peak: a speed-up in format, not in bandwidth).
+          the peak: a speed-up in format, not in bandwidth).  `alone` = the same kernel timed outside the
+          solve (burst clocks, like the measured copy peak; the long solve runs under the power cap).
 spmv_c2 : BASELINE.json configs[1], standalone SpMV on the 3-D 7-point 256^3 matrix (N=1 only); x / y
           rotate over 4 buffer pairs so no launch finds its x (134 MB, L2 evict_last) in the 126 MB L2.
 configs : (N=1 only, a few seconds) the other BASELINE configs at FULL size through the same ABI: C1
@@ -465,6 +466,26 @@ def run_gpu(args):
         "iteration_gbs_device": (2 * stream + 21 * n_loc * 8) * value / 1e9,
         "iteration_frac_of_peak": (2 * stream + 21 * n_loc * 8) * value / 1e9 / peak,
     }
+
+    # ---- the same SpMV kernel timed ALONE (burst clocks: MEASURED_PEAKS' copy figure is a burst figure too), N=1 only.
+    #      Inside the long solve the GPU runs under its power cap; this is the kernel's own roofline fraction.
+    if world == 1 and not args.no_c2:
+        xa = [1.0 + ((torch.arange(n_loc, device=dev) + 3 * j) % 17).double() / 17.0 for j in range(2)]
+        ya = [torch.empty(n_loc, dtype=torch.float64, device=dev) for _ in range(2)]
+        for j in range(3):
+            A.mul_vec_dev(xa[j % 2].data_ptr(), ya[j % 2].data_ptr())
+        torch.cuda.synchronize()
+        ea0, ea1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea0.record()
+        for j in range(10):
+            A.mul_vec_dev(xa[j % 2].data_ptr(), ya[j % 2].data_ptr())
+        ea1.record()
+        torch.cuda.synchronize()
+        ms_alone = ea0.elapsed_time(ea1) / 10
+        roofline["alone"] = {"ms": ms_alone, "gbs": stream / (ms_alone * 1e-3) / 1e9, "frac": stream / (ms_alone * 1e-3) / 1e9 / peak,
+                             "launches": 10, "note": "10 back-to-back launches of the same kernel outside the solve (x / y alternate over 2 buffer pairs; "
+                                                     "1 GB of x per launch never survives in the 126 MB L2)"}
+        del xa, ya
 
     # ---- BASELINE.json configs[1]: standalone SpMV on 256^3 7-point (N=1 only)
     spmv_c2 = None
