@@ -23,6 +23,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <type_traits>
 #include <cmath>
 #include <utility>
 #include <vector>
@@ -142,6 +143,7 @@ struct TileMeta {
   long long s4;   // 4-aligned first non-zero
   int win;        // the stage carries the x window of this tile
   int pid_off;    // index of pid[r0] inside the staged pattern-id slice; -1 => not staged
+  int halo;       // the tile may gather halo columns (a boundary tile of a partitioned matrix)
 };
 
 __host__ __device__ inline int align16i(int v) { return (v + 15) & ~15; }
@@ -266,6 +268,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
         m.r0 = r0;
         m.r1 = r1;
         m.s4 = (long long)s4;
+        m.halo = (HALO && (!a.hhead || ti >= a.first_boundary)) ? 1 : 0;  // (NCCL transport: separate launches, every listed tile)
         unsigned char* stage = smem_raw + s * STAGE_BYTES;
         if ((int64_t)(en - st) <= a.tile) {
           m.total = (int)(en - s4);
@@ -380,9 +383,13 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
         // one thread per row: x gathers go to registers (ld.global.nc through L1, L2 evict_last),
         // 8 per batch, then the sequential fold in CSR order (src/mat.rs:100-105).  Full batches
         // carry no predicates; only the last (partial) batch of a row is clamped / predicated.
+        // Partitioned matrices: only the BOUNDARY tiles have halo columns; the interior tiles (97 % of the rows of a
+        // z-slab) run the loop without the owned / halo base select (3 extra instructions per gather).
         const T* xb = a.x;
         const T* xh_adj = HALO ? (xh - a.n_local) : a.x;
         const int nl = a.n_local;
+        auto tile_rows = [&](auto halo_tile) {
+        constexpr bool HT = decltype(halo_tile)::value;
         for (int r = m.r0 + tid; r < m.r1; r += CT) {
           int p0, p1, pidv = 0;
           if (DICT)
@@ -412,7 +419,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               for (int j = 0; j < 8; ++j) c[j] = s_col[k + j];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HALO>(xb, xh_adj, nl, c[j], pol_x);
+            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HT>(xb, xh_adj, nl, c[j], pol_x);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc = add(acc, mul(xv[j], s_val[k + j]));
           }
@@ -428,7 +435,7 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
               for (int j = 0; j < 8; ++j) c[j] = s_col[min(k + j, p1 - 1)];
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HALO>(xb, xh_adj, nl, c[j], pol_x);
+            for (int j = 0; j < 8; ++j) xv[j] = gather_x<T, CONJ_IN, HT>(xb, xh_adj, nl, c[j], pol_x);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               if (k + j < p1) acc = add(acc, mul(xv[j], s_val[k + j]));
@@ -436,6 +443,11 @@ spmv_tma_kernel(const SpmvArgs<T, IP> a) {
           a.y[r] = acc;
           epilogue_acc_v<T, EPI>(acc, wv, e0, e1);
         }
+        };
+        if (HALO && m.halo)
+          tile_rows(std::true_type{});
+        else
+          tile_rows(std::false_type{});
       } else {
         // rows up to tile/2 non-zeros keep the sequential fold (read from global memory);
         // longer rows are strided over by all consumers (their summation order differs).
