@@ -264,7 +264,8 @@ struct FusedArgs {
   long long cap, max_iter;
   double tol;
   long long* stats;  // optional (SPB_FUSED_STATS=1): clocks of CTA 0 per phase, see the lap() calls
-  int slots_per_thread;  // ceil(rows_per_cta / BLOCK): shared-memory slots a thread needs per vector
+  int slots;             // shared-memory slots per own-row vector: rows_per_cta rounded up to a warp (not to a CTA: what
+                         // shared memory does not take stays L1, where the matrix lines of the CTA's rows live)
   unsigned poll_sleep;   // ns between two polls of the grid barrier (0: spin)
   int rows_per_cta;      // R
   int bw_lo, bw_hi;      // max (row - col), max (col - row) over the matrix (MODE 2)
@@ -272,11 +273,6 @@ struct FusedArgs {
   int mat_cap;           // MODE 2: matrix entries of a CTA's rows that fit its shared memory (0: matrix stays in global memory)
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -499,7 +495,7 @@ __global__ void __launch_bounds__(BLOCK, 1) bicg_fused_kernel(const FusedArgs<T>
   int rp = 0;  // reduction points cycle through three slot buffers (two inboxes in MODE 3)
   scal2 red[2];
   // own-row vectors: shared memory (slot = local row) or global (index = row)
-  const int slots = a.slots_per_thread * BLOCK;
+  const int slots = a.slots;
   T* const sm = reinterpret_cast<T*>(fused_smem);
   T* const r_v = SV ? sm : a.r;
   T* const r0_v = SV ? sm + slots : a.r0;
@@ -1205,7 +1201,8 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
       const int gc = (int)std::max<int64_t>(1, std::min<int64_t>(kFusedCluster, ceil_div(n, BLOCK)));
       const int R = (int)ceil_div(n, (int64_t)gc);
       const int spt = (int)ceil_div((int64_t)R, (int64_t)BLOCK);
-      const size_t smem_sv = (per_slot * (size_t)spt * BLOCK + 15) / 16 * 16;
+      const int slots = (R + 31) & ~31;
+      const size_t smem_sv = (per_slot * (size_t)slots + 15) / 16 * 16;
       const int64_t win_elems = (int64_t)R + fa.bw_lo + fa.bw_hi;
       const size_t smem_win = (smem_sv + (size_t)win_elems * sizeof(T) + 31) / 16 * 16;
       // matrix slice: mean entries per CTA + 25 % (a CTA whose slice is larger reads its matrix from global memory)
@@ -1236,7 +1233,7 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
                         cudaFuncSetAttribute(kern_cl, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                         cudaOccupancyMaxActiveClusters(&nclusters, kern_cl, &cfg) == cudaSuccess && nclusters >= 1;
         if (ok) {
-          fa.slots_per_thread = spt;
+          fa.slots = slots;
           fa.rows_per_cta = R;
           fa.win_elems = (int)win_elems;
           fa.mat_cap = (int)mat_cap;
@@ -1250,10 +1247,10 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
     // ---- MODE 0 / 1: cooperative grid, one CTA per SM (the shared-memory variant needs most of an SM's shared memory anyway)
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(c->sm_count, kFusedMaxGrid), ceil_div(n, BLOCK)));
     const int R = (int)ceil_div(n, (int64_t)grid);
-    const int spt = (int)ceil_div((int64_t)R, (int64_t)BLOCK);
-    const size_t smem_sv = (per_slot * (size_t)spt * BLOCK + 15) / 16 * 16 + 64;
+    const int slots = (R + 31) & ~31;
+    const size_t smem_sv = (per_slot * (size_t)slots + 15) / 16 * 16 + 64;
     const bool sv = allow_smem && smem_sv + 4096 <= (size_t)smem_cap;
-    fa.slots_per_thread = spt;
+    fa.slots = slots;
     fa.rows_per_cta = R;
     fa.win_elems = 0;
     fa.mat_cap = 0;
