@@ -5,6 +5,8 @@
     python tools/ncu_targets.py c4      7-point 200^3 complex128 (plain CSR stream)
     python tools/ncu_targets.py c5f32   27-point 384^3 f32 (dictionary stream, 4 bytes per non-zero)
     python tools/ncu_targets.py k3      Jacobi-BiCGStab on 27-point 384^3, 4 iterations (bicg_k1 / k2 / k3)
+    python tools/ncu_targets.py gs      symmetric Gauss-Seidel apply on 7-point 128^3 (gs_wave_kernel; use --replay-mode application)
+    python tools/ncu_targets.py fused   single-kernel BiCGStab on the 100^2 reference matrix (cluster mode)
 """
 import os
 import sys
@@ -67,3 +69,23 @@ elif what == "k3":
         pass
     ctx.synchronize()
     print("k3 done")
+
+if what == "gs":
+    g = 128
+    A = sp.GpuCsrMat.from_stencil(sp.STENCIL_LAP3D7, g, g, g, params=(0.05,))
+    M = sp.GaussSeidelPrecond(A, symmetric=True)
+    r = torch.rand(g**3, dtype=torch.float64, device=dev)
+    z = torch.empty_like(r)
+    M.mul_vec_dev(r.data_ptr(), z.data_ptr())
+    ctx.synchronize()
+    print(what, M.schedule_info(), float(z.sum()))
+elif what == "fused":
+    g = 100
+    A = sp.GpuCsrMat.from_stencil(sp.STENCIL_DIRICHLET2D, g, g, 1)
+    ii, jj = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+    border = (ii == 0) | (ii == g - 1) | (jj == 0) | (jj == g - 1)
+    rhs = torch.from_numpy(np.where(border, (ii + jj).astype(np.float64), 0.0).ravel()).to(dev)
+    x = torch.zeros(g * g, dtype=torch.float64, device=dev)
+    M = sp.DiagPrecond.from_matrix(A)
+    S = sp.BiCGStab(A, g * g)
+    print(what, S.solve_dev(rhs.data_ptr(), x.data_ptr(), 10000, 1e-8, precond=M))
