@@ -1168,8 +1168,7 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
   const int block = be && *be ? atoi(be) : 512;
   const char* se = getenv("SPB_FUSED_SMEM");
   const bool allow_smem = !(se && *se == '0');
-  const char* we = getenv("SPB_FUSED_WIN");
-  const bool allow_win = allow_smem && !(we && *we == '0');
+  const bool allow_win = allow_smem;  // (the cluster mode keeps the own-row vectors in shared memory too)
   int smem_cap = 0;
   SPB_CUDA(cudaDeviceGetAttribute(&smem_cap, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   if (allow_win && band_lo < 0) {  // bandwidth of the matrix: decides whether the gathered vector fits a shared-memory window

@@ -23,11 +23,10 @@ for g in [int(v) for v in os.environ.get("TUNE_GRIDS", "100,256,512").split(",")
     M = sp.DiagPrecond.from_matrix(A)
     S = sp.BiCGStab(A, g * g)
     for block in (256, 512):
-        for mode, (smem, win, cl) in {"smem": ("1", "1", "0"), "cluster": ("1", "1", "1")}.items():
+        for mode, (smem, win, cl) in {"smem": ("1", "", "0"), "cluster": ("1", "", "1")}.items():
             os.environ["SPB_FUSED_CLUSTER"] = cl
             os.environ["SPB_FUSED_BLOCK"] = str(block)
             os.environ["SPB_FUSED_SMEM"] = smem
-            os.environ["SPB_FUSED_WIN"] = win
             x.zero_()
             print(f"grid {g} block {block} {mode}:", file=sys.stderr, flush=True)
             S.solve_dev(rhs.data_ptr(), x.data_ptr(), 10000, 1e-8, precond=M)

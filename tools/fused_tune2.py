@@ -25,12 +25,11 @@ for g in grids:
     S = sp.BiCGStab(A, g * g)
     ref = None
     for block in (256, 512):
-        for mode, (smem, win, cl) in {"global": ("0", "1", "0"), "smem": ("1", "1", "0"), "cluster": ("1", "1", "1")}.items():
+        for mode, (smem, win, cl) in {"global": ("0", "", "0"), "smem": ("1", "", "0"), "cluster": ("1", "", "1")}.items():
             os.environ["SPB_FUSED"] = "1"
             os.environ["SPB_FUSED_CLUSTER"] = cl
             os.environ["SPB_FUSED_BLOCK"] = str(block)
             os.environ["SPB_FUSED_SMEM"] = smem
-            os.environ["SPB_FUSED_WIN"] = win
             ts = []
             for _ in range(4):
                 x.zero_()
@@ -48,7 +47,6 @@ for g in grids:
         os.environ["SPB_FUSED_STATS"] = "1"
         os.environ["SPB_FUSED_BLOCK"] = "512"
         os.environ["SPB_FUSED_SMEM"] = "1"
-        os.environ["SPB_FUSED_WIN"] = "1"
         x.zero_()
         S.solve_dev(rhs.data_ptr(), x.data_ptr(), 10000, 1e-8, precond=M)
         os.environ.pop("SPB_FUSED_STATS")
