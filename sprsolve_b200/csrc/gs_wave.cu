@@ -1075,7 +1075,8 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   };
   if (ws.cluster < 0) {
     // First sweep of this schedule: which launch shape is fastest depends on how the blocks map onto the GPCs
-    // (measured on B200: 7-point 100^3, 100 blocks: clusters of 16 are 13 % faster; 128^3, 128 blocks: 2-5 % slower).
+    // (measured on B200, 7-point: 100^3, 100 blocks: clusters of 16 are 13 % faster; 128^3, 128 blocks: clusters of 16 / 8 are
+    // 2-5 % slower -- not all of them fit at once -- and clusters of 4 are 10 % faster).
     // A sweep is a pure function of its inputs (the pre-pass resets mailbox and ticket), so it is simply run with each
     // candidate and timed -- same bits whatever is chosen.  SPB_GS_CLUSTER fixes the choice.
     const char* ce = getenv("SPB_GS_CLUSTER");
@@ -1089,7 +1090,7 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
       SPB_CUDA(cudaEventCreate(&e1));
       float best_ms = 0.f;
       int best = 0, last_used = -1;
-      for (int cand : {16, 8, 0}) {
+      for (int cand : {16, 8, 4, 2, 0}) {
         const int used = run(cand);  // warm-up, and what the device really grants
         if (used == last_used) continue;
         last_used = used;
