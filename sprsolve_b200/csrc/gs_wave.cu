@@ -96,7 +96,7 @@ __host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, in
   off += wave_a16(4LL * Wm * nrows);
   L.hslot = off;  // sentinel-filled landing slots of the cross-block values (mailbox order)
   off += wave_a16((long long)sizeof(T) * nhalo);
-  L.hcol = off;  // the column of every landing slot (cluster mode: which CTA's shared memory holds it)
+  L.hcol = off;  // producer of every landing slot, block << 16 | row in block (cluster mode: whose shared memory holds it)
   off += wave_a16(4LL * nhalo);
   L.total = off;
   return L;
@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
     wv_cluster_sync();
     return;
   }
+  const int cshift = 31 - __clz((int)csize);  // log2(cluster size)
   const int b = BWD ? a.nblocks - 1 - t : t;
   const int r0 = b * a.block_rows;
   const int c0 = a.blk_chunk[t], c1 = a.blk_chunk[t + 1];
@@ -405,13 +406,13 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
         const T* mbox = a.mailbox + (((long long)hdr[7] << 32) | (unsigned)hdr[6]);  // this chunk's slots: contiguous
         // where slot h is polled: the producer's shared-memory x block when it runs in this cluster, else the mailbox
         auto poll = [&](int h, uint32_t ra) -> T { return (CL && ra) ? wv_poll_remote<T>(ra) : wv_poll(mbox + h); };
-        auto remote_of = [&](int h) -> uint32_t {
+        auto remote_of = [&](int h) -> uint32_t {  // (cluster sizes are powers of two: shifts, no division)
           if (!CL) return 0u;
-          const int j = hcol[h];
-          const int pb = j / a.block_rows;
+          const unsigned w = (unsigned)hcol[h];  // producer block << 16 | row inside that block
+          const int pb = (int)(w >> 16);
           const int tp = BWD ? a.nblocks - 1 - pb : pb;
-          if (tp / (int)csize != t / (int)csize) return 0u;
-          return wv_mapa(smem_u32(xs + (j - pb * a.block_rows)), (uint32_t)(tp % (int)csize));
+          if ((tp >> cshift) != (t >> cshift)) return 0u;
+          return wv_mapa(smem_u32(xs + (w & 0xFFFFu)), (uint32_t)(tp & ((int)csize - 1)));
         };
         // slots are sorted by need; thread t polls slots t, t + NH, ...: coalesced, and every thread starts early
         for (int h0 = htid; h0 < nhalo; h0 += WAVE_NH * WAVE_HB) {
@@ -639,6 +640,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
   const int64_t nb = ceil_div(n, R);
   ws.block_rows = (int)R;
   ws.nblocks = (int)nb;
+  if (R > 65535 || nb > 65535) ws.cluster = 0;  // (the packed producer words of the cluster mode hold 16 bits each)
   const size_t ring_off = (size_t)WAVE_FIXED + ((size_t)R * sizeof(T) + 127) / 128 * 128;
   ws.smem_bytes = ring_off + (size_t)ws.stages * stage_bytes;
 
@@ -934,7 +936,14 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
       put_bytes(stat, base + L.eval, ev.data(), ev.size());
       put_bytes(stat, base + L.mail, mail.data(), mail.size());
       put_bytes(stat, base + L.hslot, hs.data(), hs.size());
-      put_bytes(stat, base + L.hcol, plan_halo.data() + pl.hal_beg, nhalo);
+      {  // where every landing slot's value is produced: block << 16 | row inside the block (cluster mode)
+        std::vector<unsigned> hw(nhalo);
+        for (int h = 0; h < nhalo; ++h) {
+          const int64_t j = plan_halo[pl.hal_beg + h];
+          hw[h] = (unsigned)((j / R) << 16) | (unsigned)(j % R);
+        }
+        put_bytes(stat, base + L.hcol, hw.data(), nhalo);
+      }
       chunks[ci] = d;
     }
   };
