@@ -73,7 +73,8 @@ __host__ __device__ inline unsigned long long wave_sentinel_fill() {
 __host__ __device__ inline int wave_a16(long long v) { return (int)((v + 15) & ~15LL); }
 
 // Byte offsets of the sections of one packed chunk (all 16-byte aligned).
-// header (32 B): nrows, nseg, W, nhalo, Wo, Wm, mailbox offset (lo, hi)
+// header (64 B): nrows, nseg, W, nhalo, Wo, Wm, mailbox offset (lo, hi); then the byte offsets of the sections
+// (seg_end, rowid, diag, eoff, eval, mail, hslot, hcol)
 #define SPB_WAVE_NOMAIL 0xFFFFFFFFu
 struct WaveLayout {
   int seg_end, rowid, diag, eoff, eval, mail, hslot, hcol, total;
@@ -81,7 +82,7 @@ struct WaveLayout {
 template <typename T>
 __host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, int nhalo, int Wm) {
   WaveLayout L;
-  int off = 32;
+  int off = 64;  // header: 8 ints of sizes + the 8 section offsets below (the kernel reads them instead of recomputing)
   L.seg_end = off;
   off += wave_a16(4LL * nseg);
   L.rowid = off;
@@ -99,6 +100,22 @@ __host__ __device__ inline WaveLayout wave_layout(int nrows, int nseg, int W, in
   L.hcol = off;  // producer of every landing slot, block << 16 | row in block (cluster mode: whose shared memory holds it)
   off += wave_a16(4LL * nhalo);
   L.total = off;
+  return L;
+}
+
+// the layout of a staged chunk as the analysis stored it in the header (two 16-byte shared-memory loads)
+__device__ __forceinline__ WaveLayout wave_layout_of(const int* hdr) {
+  const int4 a = *reinterpret_cast<const int4*>(hdr + 8), b = *reinterpret_cast<const int4*>(hdr + 12);
+  WaveLayout L;
+  L.seg_end = a.x;
+  L.rowid = a.y;
+  L.diag = a.z;
+  L.eoff = a.w;
+  L.eval = b.x;
+  L.mail = b.y;
+  L.hslot = b.z;
+  L.hcol = b.w;
+  L.total = 0;
   return L;
 }
 
@@ -400,7 +417,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
       const int* hdr = reinterpret_cast<const int*>(st);
       const int nhalo = hdr[3];
       if (nhalo > 0) {
-        const WaveLayout L = wave_layout<T>(hdr[0], hdr[1], hdr[2], nhalo, hdr[5]);
+        const WaveLayout L = wave_layout_of(hdr);
         T* hslot = reinterpret_cast<T*>(st + L.hslot);
         const int* hcol = reinterpret_cast<const int*>(st + L.hcol);
         const T* mbox = a.mailbox + (((long long)hdr[7] << 32) | (unsigned)hdr[6]);  // this chunk's slots: contiguous
@@ -469,7 +486,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
     const unsigned char* st = ring + (size_t)s * a.stage_bytes;
     const int* hdr = reinterpret_cast<const int*>(st);
     const int nrows = hdr[0], nseg = hdr[1], W = hdr[2], Wo = hdr[4], Wm = hdr[5];
-    const WaveLayout L = wave_layout<T>(nrows, nseg, W, hdr[3], Wm);
+    const WaveLayout L = wave_layout_of(hdr);
     const uint32_t* mail = reinterpret_cast<const uint32_t*>(st + L.mail);
     const int* seg_end = reinterpret_cast<const int*>(st + L.seg_end);
     const int* rowid = reinterpret_cast<const int*>(st + L.rowid);
@@ -927,8 +944,9 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
           aux_dims[2 * slot + 1] = Wo;
         }
       }
-      const int hdr[8] = {nrows, nseg, W, nhalo, Wo, Wm, (int)(unsigned)(pl.mb_off & 0xffffffffLL), (int)(pl.mb_off >> 32)};
-      put_bytes(stat, base, hdr, 8);
+      const int hdr[16] = {nrows, nseg, W, nhalo, Wo, Wm, (int)(unsigned)(pl.mb_off & 0xffffffffLL), (int)(pl.mb_off >> 32),
+                           L.seg_end, L.rowid, L.diag, L.eoff, L.eval, L.mail, L.hslot, L.hcol};
+      put_bytes(stat, base, hdr, 16);
       put_bytes(stat, base + L.seg_end, plan_segs.data() + pl.seg_beg, nseg);
       put_bytes(stat, base + L.rowid, plan_rows.data() + pl.row_beg, nrows);
       put_bytes(stat, base + L.diag, dg.data(), nrows);
