@@ -481,6 +481,10 @@ def test_gauss_seidel_input_equal_to_the_handoff_sentinel(sp, orc):
     {"SPB_GS_BLOCK_ROWS": "7"},                                               # almost every dependency crosses blocks (polls)
     {"SPB_GS_BLOCK_ROWS": "96", "SPB_GS_STAGE_ROWS": "8", "SPB_GS_STAGE_BYTES": "1024", "SPB_GS_STAGE_OTHER": "64"},  # levels split over chunks
     {"SPB_GS_BLOCK_ROWS": "33", "SPB_GS_STAGES": "2"},
+    {"SPB_GS_CLUSTER": "0"},                                                  # plain CTAs + global mailbox only
+    {"SPB_GS_CLUSTER": "16"},                                                 # one cluster of 16 with padding CTAs, DSMEM polls
+    {"SPB_GS_CLUSTER": "4", "SPB_GS_BLOCK_ROWS": "33"},                       # many clusters: DSMEM inside, mailbox between them
+    {"SPB_GS_CLUSTER": "2", "SPB_GS_BLOCK_ROWS": "7"},
     {"SPB_GS_LEGACY": "1"},                                                   # fallback: global levels + grid barrier
 ])
 def test_gauss_seidel_wavefront_schedules(sp, orc, knobs, monkeypatch):
