@@ -461,6 +461,10 @@ def run_gpu(args):
         "csr_equivalent_bytes_per_launch": b_spmv, "csr_equivalent_gbs": csr_eq, "csr_equivalent_frac": csr_eq / peak,
         "plan": {k: plan[k] for k in ("consumer_threads", "stages", "tile_nnz", "ctas_per_sm")},
         "bytes_per_launch": stream, "avg_launch_ms": avg_ms, "launches_timed": n_spmv, "products_timed": n_products,
+        # the launches inside the solve are the epilogue variants: they also read the dot-product operand (r0 / r, one more
+        # n-vector) that `bytes_per_launch` -- the bare product -- does not count; `frac` stays the conservative figure
+        "epilogue_operand_bytes_per_launch": n_loc * 8,
+        "frac_incl_epilogue_operand": (stream + n_loc * 8) / (avg_ms * 1e-3) / 1e9 / peak,
         "step_share": {"spmv_ms": ms_spmv, "vector_ms": ms_vec, "scalar_ms": ms_sc, "spmv_launches": n_spmv, "vector_launches": n_vec, "scalar_launches": n_sc},
         "iteration_bytes_model": 2 * stream + 21 * n_loc * 8,
         "iteration_gbs_device": (2 * stream + 21 * n_loc * 8) * value / 1e9,
