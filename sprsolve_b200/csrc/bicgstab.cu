@@ -1165,7 +1165,8 @@ void BicgStab<T>::launch_fused(const FusedArgs<T>& fa0, int64_t n) {
   Ctx* c = ctx;
   FusedArgs<T> fa = fa0;
   const char* be = getenv("SPB_FUSED_BLOCK");
-  const int block = be && *be ? atoi(be) : 512;
+  // 512 threads per CTA; 256 for the smallest systems (<= 8192 rows: 64^2 7.6 vs 8.1 us per iteration in cluster mode)
+  const int block = be && *be ? atoi(be) : (n <= 8192 ? 256 : 512);
   const char* se = getenv("SPB_FUSED_SMEM");
   const bool allow_smem = !(se && *se == '0');
   const bool allow_win = allow_smem;  // (the cluster mode keeps the own-row vectors in shared memory too)
