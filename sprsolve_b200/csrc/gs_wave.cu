@@ -300,6 +300,7 @@ struct WaveArgs {
   int gate_value;
   int* err;  // Ctx::dev_err
   unsigned spin_ns;  // back-off of a row thread that waits for a value of another block
+  T* sig;            // forward sweep of the symmetric apply: the fold over the lower entries of every row, for the backward pre-pass
 };
 
 // Pre-pass (fully parallel): sentinel-fill the mailbox, permute rhs into sweep order, reduce the other
@@ -308,7 +309,7 @@ template <typename T, typename IP, bool BWD>
 __global__ void __launch_bounds__(kVecThreads) gs_wave_prep_kernel(int64_t mb8, unsigned long long* mailbox8, int64_t rhs_slots, const int* rowmap,
                                                                     const T* rhs, T* rhsp, const T* other, const IP* indptr, const int* cols,
                                                                     const T* vals, T* aux, const long long* aux_base, const int* aux_dims,
-                                                                    int* ticket, const int* gate, int gate_value) {
+                                                                    int* ticket, const int* gate, int gate_value, const T* sig) {
   if (gate && *gate != gate_value) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) ticket[0] = 0;
   SPB_GRID_STRIDE(i, mb8) mailbox8[i] = wave_sentinel_fill<T>();
@@ -316,7 +317,11 @@ __global__ void __launch_bounds__(kVecThreads) gs_wave_prep_kernel(int64_t mb8, 
     const int r = rowmap[p];
     rhsp[p] = r >= 0 ? rhs[r] : zero_of<T>();
     if (!other) continue;
-    if (BWD) {  // lower entries come first in CSR order: fold them now (src/gauss_seidel.rs:113-118)
+    if (BWD && sig) {
+      // symmetric apply: `other` is the forward sweep's result, and that sweep has just folded exactly these entries
+      // in exactly this order (its own sigma of row r) -- take its value instead of traversing the matrix again
+      aux[p] = r >= 0 ? sig[r] : zero_of<T>();
+    } else if (BWD) {  // lower entries come first in CSR order: fold them now (src/gauss_seidel.rs:113-118)
       T sigma = zero_of<T>();
       if (r >= 0)
         for (IP k = indptr[r]; k < indptr[r + 1]; ++k) {
@@ -521,6 +526,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) gs_wave_kernel(const WaveArgs
           sigma = add(sigma, mul(v2, x2));
           sigma = add(sigma, mul(v3, x3));
         }
+        if (!BWD && a.sig) a.sig[row] = sigma;  // (the backward sweep of the symmetric apply starts from this fold)
         if (!BWD && a.aux)
           for (int e = 0; e < Wo; ++e) sigma = add(sigma, auxs[e * nrows + i]);
         const T x = divi(sub(rv, sigma), dv);  // src/gauss_seidel.rs:123
@@ -1008,7 +1014,7 @@ void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<
 }
 
 template <typename T, typename IP>
-static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other) {
+static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, const T* sig) {
   Ctx* c = M->ctx;
   CsrMat<T>* A = M->A;
   const int64_t mb8 = (ws.mailbox_slots * (int64_t)sizeof(T) + 7) / 8;  // (the allocation carries 4 spare slots)
@@ -1018,12 +1024,12 @@ static void wave_prep_launch(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* o
   kern<<<vec_grid(c, work), kVecThreads, 0, c->stream>>>(mb8, reinterpret_cast<unsigned long long*>(ws.mailbox.p), ws.rhs_slots, bufptr<int>(ws.rowmap),
                                                           rhs, bufptr<T>(ws.rhsp), other, bufptr<IP>(A->indptr), bufptr<int>(A->cols),
                                                           bufptr<T>(A->vals), bufptr<T>(ws.aux), bufptr<long long>(ws.aux_base),
-                                                          bufptr<int>(ws.aux_dims), bufptr<int>(ws.ticket), c->gate, c->gate_value);
+                                                          bufptr<int>(ws.aux_dims), bufptr<int>(ws.ticket), c->gate, c->gate_value, sig);
   check_launch("gs_wave_prep_kernel");
 }
 
 template <typename T>
-void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out) {
+void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out, T* sig) {
   Ctx* c = M->ctx;
   const int64_t n = M->A->n_local;
   if (n == 0) return;
@@ -1032,9 +1038,9 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   const int stage_bytes = (ws.stage_static + rhs_bytes + oth_bytes + 127) / 128 * 128;
   auto prep = [&]() {
     if (M->A->ip64)
-      wave_prep_launch<T, int64_t>(M, ws, rhs, other);
+      wave_prep_launch<T, int64_t>(M, ws, rhs, other, ws.backward ? sig : nullptr);
     else
-      wave_prep_launch<T, int32_t>(M, ws, rhs, other);
+      wave_prep_launch<T, int32_t>(M, ws, rhs, other, ws.backward ? sig : nullptr);
   };
   WaveArgs<T> a{};
   a.stat = bufptr<unsigned char>(ws.stat);
@@ -1055,6 +1061,7 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
   a.gate = c->gate;
   a.gate_value = c->gate_value;
   a.err = c->dev_err;
+  a.sig = ws.backward ? nullptr : sig;
   {
     const char* se = getenv("SPB_GS_SPIN_NS");
     a.spin_ns = se && *se ? (unsigned)atoi(se) : 0u;
@@ -1144,7 +1151,7 @@ void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out)
 #define SPB_INST_WAVE(T)                                                                                              \
   template void wave_build<T>(CsrMat<T>*, const std::vector<int64_t>&, const std::vector<int>&, const std::vector<T>&, \
                               bool, WaveSched&);                                                                      \
-  template void wave_sweep<T>(GsOp<T>*, WaveSched&, const T*, const T*, T*);
+  template void wave_sweep<T>(GsOp<T>*, WaveSched&, const T*, const T*, T*, T*);
 SPB_INST_WAVE(double)
 SPB_INST_WAVE(cplx)
 SPB_INST_WAVE(float)

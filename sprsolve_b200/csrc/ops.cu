@@ -435,6 +435,14 @@ void gs_apply(GsOp<T>* M, const T* in, T* out) {
     sweep<T>(M, M->fwd, in, out, nullptr, out);
   } else {
     T* tmp = bufptr<T>(M->tmp);
+    if (M->wfwd.ok && M->wbwd.ok && in != tmp && out != tmp) {
+      // both sweeps on the wavefront path: the forward sweep hands its fold over the lower entries of every row to the
+      // backward sweep, whose pre-pass would otherwise traverse the matrix once more to compute the very same sums
+      if (!M->sig.p) M->sig.alloc(sizeof(T) * (size_t)std::max<int64_t>(M->A->n_local, 1));
+      wave_sweep<T>(M, M->wfwd, in, nullptr, tmp, bufptr<T>(M->sig));
+      wave_sweep<T>(M, M->wbwd, in, tmp, out, bufptr<T>(M->sig));
+      return;
+    }
     sweep<T>(M, M->fwd, in, tmp, nullptr, tmp);       // forward sweep from zero
     sweep<T>(M, M->bwd, in, tmp, out, out, tmp);      // rows n-1..0: lower cols = forward values (relaxed: mixed with them)
   }

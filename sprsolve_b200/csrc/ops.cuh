@@ -71,6 +71,7 @@ struct GsOp : spb_op {
   bool levels_ready = false;
   WaveSched wfwd, wbwd; // block-wavefront schedules (the fast path)
   DevBuf tmp;           // T [n]: forward result for the symmetric variant
+  DevBuf sig;           // T [n]: the forward sweep's fold over the lower entries (the backward sweep starts from it)
   DevBuf barrier;       // grid barrier words
   DevBuf wave_stats;    // int64 [4 * nblocks] per-block clocks of the last wavefront sweep (SPB_GS_STATS=1)
   int64_t bad_row = -1; // first row with a missing / tiny diagonal (src/gauss_seidel.rs:72-78)
@@ -102,7 +103,7 @@ template <typename T>
 void wave_build(CsrMat<T>* A, const std::vector<int64_t>& ip, const std::vector<int>& cols,
                 const std::vector<T>& vals, bool backward, WaveSched& ws);
 template <typename T>
-void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out);
+void wave_sweep(GsOp<T>* M, WaveSched& ws, const T* rhs, const T* other, T* out, T* sig = nullptr);
 
 // Generic operator application used by the solvers: CSR -> SpMV, Diag, GS.
 template <typename T>
