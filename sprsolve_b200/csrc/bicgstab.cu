@@ -935,6 +935,7 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
   scal2* redp = bufptr<scal2>(red);
   Acc<T>* parts = bufptr<Acc<T>>(partials);
   const int grid = vec_grid(c, n);
+  const int grid_r = std::min(vec_grid_resident(c, n, bicg_k3<T>), vec_grid_resident(c, n, bicg_k_init<T>));  // kernels with partial sums
   const long long cap = hist ? std::min<int64_t>(hist_cap, max_iter + 1) : 0;
   double* hd = nullptr;
   if (cap > 0) {
@@ -1012,14 +1013,14 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     check_launch("bicg scalar kernel");
   };
   auto reduce_vec = [&]() {  // per-block partials of a vector kernel -> red (all ranks)
-    finalize_allreduce<T>(c, parts, grid, redp);
+    finalize_allreduce<T>(c, parts, grid_r, redp);
   };
   auto reduce_spmv = [&](auto tail) {  // epilogue partials of the last SpMV -> Am->red (all ranks), then the scalar step
     finalize_reduce_tail<T>(c, bufptr<Acc<T>>(Am->partials), Am->last_partial_blocks, bufptr<scal2>(Am->red), true, tail);
   };
   auto k_init = [&](int restart) {
     LaunchScope ls(c, FAM_VEC);
-    bicg_k_init<T><<<grid, kVecThreads, 0, c->stream>>>(st, restart, n, rhs, r, r0, parts);
+    bicg_k_init<T><<<grid_r, kVecThreads, 0, c->stream>>>(st, restart, n, rhs, r, r0, parts);
     check_launch("bicg_k_init");
   };
   auto k1 = [&](bool first) {
@@ -1058,7 +1059,7 @@ int BicgStab<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_
     reduce_spmv(BicgS3Tail<T>{st, bufptr<scal2>(Am->red)});                 // + w = <t, r> / <t, t>
     {
       LaunchScope ls(c, FAM_VEC);
-      bicg_k3<T><<<grid, kVecThreads, 0, c->stream>>>(st, n, x, y, z, r, t, r0, parts);
+      bicg_k3<T><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, x, y, z, r, t, r0, parts);
       check_launch("bicg_k3");
     }
     reduce_vec();

@@ -283,6 +283,11 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
   scal2* red2p = bufptr<scal2>(red2);
   Acc<T>* parts = bufptr<Acc<T>>(partials);
   const int grid = vec_grid(c, n);
+  // the kernels that carry partial sums (40-48 registers): one wave of resident CTAs (vecops.cuh: vec_grid_resident)
+  int grid_r = vec_grid_resident(c, n, mr_k1<T, T, true>);
+  grid_r = std::min(grid_r, vec_grid_resident(c, n, mr_k1<T, T, false>));
+  grid_r = std::min(grid_r, vec_grid_resident(c, n, mr_k_init<T, T, true>));
+  grid_r = std::min(grid_r, vec_grid_resident(c, n, mr_k_init<T, T, false>));
   const long long cap = hist ? std::min<int64_t>(hist_cap, max_iter) : 0;
   double* hd = nullptr;
   if (cap > 0) {
@@ -301,7 +306,7 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
     check_launch("minres scalar kernel");
   };
   auto reduce_vec = [&]() {
-    finalize_allreduce<T>(c, parts, grid, redp);
+    finalize_allreduce<T>(c, parts, grid_r, redp);
   };
   // b2 = <v_new, w_new> for a generic preconditioner (separate apply + conj_dot)
   auto generic_b2 = [&](T* vn, T* wn) {
@@ -332,11 +337,11 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
     {
       LaunchScope ls(c, FAM_VEC);
       if (pcm == PCM_JACOBI)
-        mr_k_init<T, T, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const T*)dinv, parts);
+        mr_k_init<T, T, true><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const T*)dinv, parts);
       else if (pcm == PCM_JACOBI_REAL)
-        mr_k_init<T, real_t<T>, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const real_t<T>*)dinv, parts);
+        mr_k_init<T, real_t<T>, true><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const real_t<T>*)dinv, parts);
       else
-        mr_k_init<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const T*)nullptr, parts);
+        mr_k_init<T, T, false><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, rhs, v_old, v_new, v, p_old, p, w_new, (const T*)nullptr, parts);
       check_launch("mr_k_init");
     }
     reduce_vec();
@@ -372,11 +377,11 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
           {
             LaunchScope ls(c, FAM_VEC);
             if (pcm == PCM_JACOBI)
-              mr_k1<T, T, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)dinv, parts);
+              mr_k1<T, T, true><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)dinv, parts);
             else if (pcm == PCM_JACOBI_REAL)
-              mr_k1<T, real_t<T>, true><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const real_t<T>*)dinv, parts);
+              mr_k1<T, real_t<T>, true><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const real_t<T>*)dinv, parts);
             else
-              mr_k1<T, T, false><<<grid, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)nullptr, parts);
+              mr_k1<T, T, false><<<grid_r, kVecThreads, 0, c->stream>>>(st, n, v_new, v_old, v, w_new, (const T*)nullptr, parts);
             check_launch("mr_k1");
           }
           if (pcm == PCM_GENERIC) {  // beta^2 = <v_new, M v_new> needs the operator in between: not fused
@@ -384,9 +389,9 @@ int MinRes<T>::solve_dev(spb_op* M, const void* d_rhs, void* d_x, int64_t max_it
             generic_b2(v_new, w_new);
             scalar(mr_s_givens<T, false>, st, redp, b2src, 1, (long long)its, hd, cap);
           } else if (cs) {
-            finalize_reduce_tail<T>(c, parts, grid, redp, true, MrGivensTail<T, true>{st, redp, b2src, 0, (long long)its, hd, cap});
+            finalize_reduce_tail<T>(c, parts, grid_r, redp, true, MrGivensTail<T, true>{st, redp, b2src, 0, (long long)its, hd, cap});
           } else {
-            finalize_reduce_tail<T>(c, parts, grid, redp, true,
+            finalize_reduce_tail<T>(c, parts, grid_r, redp, true,
                                     MrGivensTail<T, false>{st, redp, b2src, precond ? 1 : 0, (long long)its, hd, cap});
           }
           T* pt = p_oold;

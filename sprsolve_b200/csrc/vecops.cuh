@@ -15,6 +15,16 @@ inline int vec_grid(const Ctx* c, int64_t n) {
   return (int)std::max<int64_t>(1, std::min(want, cap));
 }
 inline int64_t vec_max_grid(const Ctx* c) { return (int64_t)c->sm_count * 8; }
+// Grid of a vector kernel that does not fit 8 CTAs per SM (the kernels that also carry double-double partial sums use
+// 40-48 registers: 5-6 resident CTAs): exactly ONE wave of resident CTAs.  With the fixed 8 per SM such a kernel ran
+// 1.6 waves, the second one 60 % full (bicg_k3: 5.2 TB/s where bicg_k1 / k2 reach 6.2-6.3, profiles/r02_bicg_k_ncu_full.json).
+template <typename K>
+inline int vec_grid_resident(const Ctx* c, int64_t n, K kernel) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kVecThreads, 0) != cudaSuccess || nb < 1) nb = 8;
+  const int64_t cap = (int64_t)c->sm_count * std::min(nb, 8);
+  return (int)std::max<int64_t>(1, std::min(ceil_div(n, (int64_t)kVecThreads), cap));
+}
 
 #define SPB_GRID_STRIDE(i, n)                                                        \
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n);          \
