@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(kVecThreads) vec_reduce_k(int64_t n, const T* 
 
 template <typename T>
 void vec_reduce(Ctx* c, int kind, int64_t n, const T* x, const T* y, Acc<T>* partials, scal2* red, bool allreduce) {
-  const int grid = vec_grid(c, n);
+  // one wave of resident CTAs (the complex instances hold 40-44 registers: vecops.cuh, vec_grid_resident)
+  const int grid = kind == 0 ? vec_grid_resident(c, n, vec_reduce_k<T, 0>) : kind == 1 ? vec_grid_resident(c, n, vec_reduce_k<T, 1>)
+                                                                                        : vec_grid_resident(c, n, vec_reduce_k<T, 2>);
   {
     LaunchScope ls(c, FAM_VEC);
     if (kind == 0)
